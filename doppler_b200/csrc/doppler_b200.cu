@@ -1,0 +1,659 @@
+// doppler_b200.cu -- C ABI (include/doppler_b200.h) over the sm_100a mixer kernels.
+//
+// Host side of the drop-in boundary: validates like the reference asserts (dsp.rs:87,103),
+// plans the samplenum state machine analytically (plan.h), keeps per-shift phasor tables in a
+// device arena, and drives the kernels either on caller-owned device buffers or on host
+// buffers through a 3-slot pinned/stream pipeline (H2D, kernel and D2H of neighbouring chunks
+// overlap).  No CPU implementation of the mixer exists in this library.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/doppler_b200.h"
+#include "mixer_kernels.cuh"
+#include "plan.h"
+
+using dmix::DevPiece;
+using dmix::MixArgs;
+
+namespace {
+
+constexpr uint64_t kLaunchMaxSamples = 1ull << 30;   // k fits 32 bits with room for base + offset
+constexpr uint32_t kTabMaxPeriod = 1u << 22;         // 4 Mi entries = 32 MiB: stays L2-resident
+constexpr size_t kArenaMaxEntries = 64ull << 20;     // 512 MiB of (cos, sin) pairs
+constexpr uint32_t kSmemTabMaxEntries = 4096;        // 32 KiB of shared memory per CTA at most
+constexpr size_t kHostChunkBytes = 32ull << 20;      // host-path pipeline chunk (input side)
+constexpr int kSlots = 3;
+
+std::string g_create_error;
+
+struct TableRef {
+    uint32_t off;
+    uint32_t period;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    void* d_in = nullptr;
+    void* d_out = nullptr;
+    void* h_in = nullptr;    // pinned staging
+    void* h_out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+    // pending copy-out of a staged result
+    void* user_out = nullptr;
+    size_t user_out_bytes = 0;
+    bool busy = false;
+};
+
+}  // namespace
+
+struct doppler_b200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    dplan::Planner planner;
+    float2* arena = nullptr;
+    size_t arena_cap = 0, arena_used = 0;
+    std::unordered_map<uint32_t, TableRef> tables;   // key: bits of r
+    cudaEvent_t tables_ready = nullptr;
+    bool tables_event_valid = false;
+    Slot slots[kSlots];
+    std::string err;
+    uint64_t launches = 0;
+    int occ[2][2] = {{0, 0}, {0, 0}};   // resident CTAs per SM per (in, out) variant
+};
+
+namespace {
+
+int fail(doppler_b200_ctx* ctx, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail((ctx), DOPPLER_B200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                         \
+    } while (0)
+
+inline size_t bytes_per_sample(int t) { return t == DOPPLER_B200_I16 ? 4 : 8; }
+inline bool valid_type(int t) { return t == DOPPLER_B200_I16 || t == DOPPLER_B200_F32; }
+
+using MixKernel = void (*)(const MixArgs);
+
+MixKernel mix_kernel_for(int in, int out)
+{
+    if (in == DOPPLER_B200_I16) return out == DOPPLER_B200_I16 ? dmix::mix_kernel<0, 0> : dmix::mix_kernel<0, 1>;
+    return out == DOPPLER_B200_I16 ? dmix::mix_kernel<1, 0> : dmix::mix_kernel<1, 1>;
+}
+
+// floor-division constants for x < 2^31 (Granlund-Montgomery round-up method, N = 31)
+void magic_for(uint32_t d, uint32_t* magic, uint32_t* shift)
+{
+    uint32_t l = 0;
+    while ((1ull << l) < d) l++;
+    *shift = 31 + l;
+    *magic = (uint32_t)(((1ull << (31 + l)) / d) + 1);
+}
+
+// Returns the arena offset of the phasor table for (r, period), building it on `s` if needed;
+// kNoTab when a table is not worthwhile or does not fit.
+int get_table(doppler_b200_ctx* ctx, float r, uint32_t period, uint64_t piece_len, cudaStream_t s, uint32_t* off_out)
+{
+    *off_out = dmix::kNoTab;
+    if (period > kTabMaxPeriod) return DOPPLER_B200_OK;
+    uint32_t key;
+    memcpy(&key, &r, 4);
+    auto it = ctx->tables.find(key);
+    if (it != ctx->tables.end() && it->second.period == period) {
+        *off_out = it->second.off;
+        return DOPPLER_B200_OK;
+    }
+    if (piece_len < 2ull * period) return DOPPLER_B200_OK;   // fewer reuses than entries: evaluate directly
+    const size_t entries = (size_t)period + dmix::kTabPad;
+    if (ctx->arena_used + entries > ctx->arena_cap) {
+        // grow (or recycle) the arena; cached tables are dropped, in-flight readers drained first
+        CUDA_TRY(ctx, cudaDeviceSynchronize());
+        size_t want = std::max<size_t>(ctx->arena_cap * 2, std::max<size_t>(entries * 2, 1u << 20));
+        want = std::min(want, kArenaMaxEntries);
+        if (want > ctx->arena_cap) {
+            if (ctx->arena) CUDA_TRY(ctx, cudaFree(ctx->arena));
+            ctx->arena = nullptr;
+            ctx->arena_cap = 0;
+            CUDA_TRY(ctx, cudaMalloc(&ctx->arena, want * sizeof(float2)));
+            ctx->arena_cap = want;
+        }
+        ctx->arena_used = 0;
+        ctx->tables.clear();
+        if (entries > ctx->arena_cap) return DOPPLER_B200_OK;
+    }
+    const uint32_t off = (uint32_t)ctx->arena_used;
+    const uint32_t blocks = (uint32_t)((entries + dmix::kThreads - 1) / dmix::kThreads);
+    dmix::build_phasor_table_kernel<<<blocks, dmix::kThreads, 0, s>>>(ctx->arena + off, r, period, (uint32_t)entries);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->tables_ready, s));
+    ctx->tables_event_valid = true;
+    ctx->arena_used += (entries + 1) & ~(size_t)1;   // keep 16-byte alignment of table starts
+    ctx->tables[key] = TableRef{off, period};
+    *off_out = off;
+    return DOPPLER_B200_OK;
+}
+
+// Enqueues the mixer over device buffers for a list of constant-shift runs.
+int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t nsamples, int intype, int outtype,
+               const std::vector<dplan::Run>& runs, uint32_t* samplenum, cudaStream_t s)
+{
+    if (nsamples == 0) return DOPPLER_B200_OK;
+    std::vector<dplan::Piece> pieces;
+    ctx->planner.plan(runs, 0, samplenum, &pieces);
+
+    const int G = dmix::group_samples(intype, outtype);
+    const uint32_t tile = dmix::tile_samples(intype, outtype);
+    const size_t ibps = bytes_per_sample(intype), obps = bytes_per_sample(outtype);
+    MixKernel kern = mix_kernel_for(intype, outtype);
+
+    if (ctx->tables_event_valid) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->tables_ready, 0));
+
+    size_t first_piece = 0;
+    for (uint64_t l0 = 0; l0 < nsamples; l0 += kLaunchMaxSamples) {
+        const uint64_t l1 = std::min(nsamples, l0 + kLaunchMaxSamples);
+        std::vector<DevPiece> dev;
+        uint32_t smem_entries = 0;
+        while (first_piece < pieces.size() && pieces[first_piece].k_end <= l0) first_piece++;
+        for (size_t i = first_piece; i < pieces.size() && pieces[i].k_begin < l1; i++) {
+            const dplan::Piece& pc = pieces[i];
+            const uint64_t b = std::max(pc.k_begin, l0), e = std::min(pc.k_end, l1);
+            const uint64_t delta = b - pc.k_begin;
+            DevPiece d;
+            memset(&d, 0, sizeof d);
+            d.k_begin = (uint32_t)(b - l0);
+            d.k_end = (uint32_t)(e - l0);
+            d.period = pc.period;
+            d.r = pc.r;
+            d.tab = dmix::kNoTab;
+            if (pc.period == 0) {
+                d.base = pc.base + (uint32_t)delta;
+            } else {
+                d.base = (uint32_t)(((uint64_t)pc.base + delta) % pc.period);
+                magic_for(pc.period, &d.magic, &d.shift);
+                d.step_u = (uint32_t)((uint64_t)(dmix::kThreads * G) % pc.period);
+                int rc = get_table(ctx, pc.r, pc.period, pc.k_end - pc.k_begin, s, &d.tab);
+                if (rc) return rc;
+                if (d.tab != dmix::kNoTab && pc.period <= kSmemTabMaxEntries) smem_entries = std::max(smem_entries, pc.period);
+            }
+            dev.push_back(d);
+        }
+        // get_table may have recycled the arena: offsets taken earlier in this launch would
+        // dangle.  Re-resolve every tabled piece against the final cache (cheap, rare).
+        for (DevPiece& d : dev) {
+            if (d.tab == dmix::kNoTab) continue;
+            uint32_t key;
+            memcpy(&key, &d.r, 4);
+            auto it = ctx->tables.find(key);
+            d.tab = (it != ctx->tables.end() && it->second.period == d.period) ? it->second.off : dmix::kNoTab;
+        }
+
+        MixArgs a;
+        memset(&a, 0, sizeof a);
+        a.in = static_cast<const char*>(d_in) + l0 * ibps;
+        a.out = static_cast<char*>(d_out) + l0 * obps;
+        a.tables = ctx->arena;
+        a.nsamples = (uint32_t)(l1 - l0);
+        a.npieces = (uint32_t)dev.size();
+        a.ntiles = (a.nsamples + tile - 1) / tile;
+        a.smem_entries = smem_entries;
+        DevPiece* d_pieces = nullptr;
+        if (dev.size() <= (size_t)dmix::kInlinePieces) {
+            for (size_t i = 0; i < dev.size(); i++) a.inl[i] = dev[i];
+        } else {
+            CUDA_TRY(ctx, cudaMallocAsync(&d_pieces, dev.size() * sizeof(DevPiece), s));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_pieces, dev.data(), dev.size() * sizeof(DevPiece), cudaMemcpyHostToDevice, s));
+            a.pieces = d_pieces;
+        }
+        const int occ = std::max(1, ctx->occ[intype][outtype]);
+        const uint32_t target = (uint32_t)(ctx->sm_count * occ * 4);
+        a.tiles_per_cta = std::max<uint32_t>(1, (a.ntiles + target - 1) / target);
+        const uint32_t grid = (a.ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
+        const size_t smem = smem_entries ? (smem_entries + dmix::kTabPad) * sizeof(float2) : 0;
+        kern<<<grid, dmix::kThreads, smem, s>>>(a);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+        if (d_pieces) CUDA_TRY(ctx, cudaFreeAsync(d_pieces, s));
+    }
+    return DOPPLER_B200_OK;
+}
+
+int check_common(doppler_b200_ctx* ctx, const void* in, size_t in_len, int intype, int outtype, uint32_t* samplenum,
+                 void* out, size_t out_cap, uint64_t* nsamples)
+{
+    if (!ctx) return DOPPLER_B200_EINVAL;
+    if (!valid_type(intype) || !valid_type(outtype)) return fail(ctx, DOPPLER_B200_EINVAL, "unknown IQ data type");
+    if (!samplenum) return fail(ctx, DOPPLER_B200_EINVAL, "samplenum is NULL");
+    const size_t ibps = bytes_per_sample(intype);
+    if (in_len % ibps != 0)
+        return fail(ctx, DOPPLER_B200_EALIGN, "input length %zu is not a multiple of %zu (dsp.rs assert)", in_len, ibps);
+    *nsamples = in_len / ibps;
+    if (*nsamples && (!in || !out)) return fail(ctx, DOPPLER_B200_EINVAL, "NULL buffer");
+    if (*nsamples * bytes_per_sample(outtype) > out_cap)
+        return fail(ctx, DOPPLER_B200_ECAP, "output capacity %zu < %llu bytes needed", out_cap,
+                    (unsigned long long)(*nsamples * bytes_per_sample(outtype)));
+    return DOPPLER_B200_OK;
+}
+
+int ensure_slot(doppler_b200_ctx* ctx, Slot& sl, size_t in_bytes, size_t out_bytes)
+{
+    if (!sl.stream) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    if (sl.in_cap < in_bytes) {
+        if (sl.d_in) cudaFree(sl.d_in);
+        if (sl.h_in) cudaFreeHost(sl.h_in);
+        sl.d_in = sl.h_in = nullptr;
+        sl.in_cap = 0;
+        CUDA_TRY(ctx, cudaMalloc(&sl.d_in, in_bytes));
+        CUDA_TRY(ctx, cudaMallocHost(&sl.h_in, in_bytes));
+        sl.in_cap = in_bytes;
+    }
+    if (sl.out_cap < out_bytes) {
+        if (sl.d_out) cudaFree(sl.d_out);
+        if (sl.h_out) cudaFreeHost(sl.h_out);
+        sl.d_out = sl.h_out = nullptr;
+        sl.out_cap = 0;
+        CUDA_TRY(ctx, cudaMalloc(&sl.d_out, out_bytes));
+        CUDA_TRY(ctx, cudaMallocHost(&sl.h_out, out_bytes));
+        sl.out_cap = out_bytes;
+    }
+    return DOPPLER_B200_OK;
+}
+
+bool is_pinned(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+int retire_slot(doppler_b200_ctx* ctx, Slot& sl)
+{
+    if (!sl.busy) return DOPPLER_B200_OK;
+    CUDA_TRY(ctx, cudaEventSynchronize(sl.done));
+    if (sl.user_out) memcpy(sl.user_out, sl.h_out, sl.user_out_bytes);
+    sl.user_out = nullptr;
+    sl.busy = false;
+    return DOPPLER_B200_OK;
+}
+
+// Host-buffer pipeline: chunk c uses slot c % kSlots; each slot has its own stream so the H2D
+// of chunk c+1 overlaps the kernel of chunk c and the D2H of chunk c-1.
+int mix_host(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int intype, int outtype,
+             const float* shifts, size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint32_t* samplenum,
+             void* out)
+{
+    const size_t ibps = bytes_per_sample(intype), obps = bytes_per_sample(outtype);
+    // chunk = whole number of shift blocks and of the largest tile
+    uint64_t chunk = kHostChunkBytes / ibps;
+    if (block_samples && nblocks > 1) chunk = std::max<uint64_t>(block_samples, chunk / block_samples * block_samples);
+    const bool in_pinned = is_pinned(in), out_pinned = is_pinned(out);
+    uint32_t sn = *samplenum;
+    int c = 0;
+    for (uint64_t k = 0; k < nsamples; k += chunk, c++) {
+        const uint64_t n = std::min(chunk, nsamples - k);
+        Slot& sl = ctx->slots[c % kSlots];
+        int rc = retire_slot(ctx, sl);
+        if (rc) return rc;
+        rc = ensure_slot(ctx, sl, std::min<uint64_t>(chunk, nsamples) * ibps, std::min<uint64_t>(chunk, nsamples) * obps);
+        if (rc) return rc;
+        const char* src = static_cast<const char*>(in) + k * ibps;
+        if (!in_pinned) {
+            memcpy(sl.h_in, src, n * ibps);
+            src = static_cast<const char*>(sl.h_in);
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(sl.d_in, src, n * ibps, cudaMemcpyHostToDevice, sl.stream));
+        std::vector<dplan::Run> runs;
+        if (nblocks <= 1 || block_samples == 0) {
+            runs.push_back(dplan::Run{n, dplan::ratio(shifts[0], samplerate)});
+        } else {
+            const size_t b0 = (size_t)(k / block_samples);
+            runs = dplan::runs_from_blocks(shifts + b0, nblocks - b0, block_samples, samplerate, n);
+        }
+        rc = launch_mix(ctx, sl.d_in, sl.d_out, n, intype, outtype, runs, &sn, sl.stream);
+        if (rc) return rc;
+        char* dst = static_cast<char*>(out) + k * obps;
+        if (out_pinned) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(dst, sl.d_out, n * obps, cudaMemcpyDeviceToHost, sl.stream));
+            sl.user_out = nullptr;
+        } else {
+            CUDA_TRY(ctx, cudaMemcpyAsync(sl.h_out, sl.d_out, n * obps, cudaMemcpyDeviceToHost, sl.stream));
+            sl.user_out = dst;
+            sl.user_out_bytes = n * obps;
+        }
+        CUDA_TRY(ctx, cudaEventRecord(sl.done, sl.stream));
+        sl.busy = true;
+    }
+    for (int i = 0; i < kSlots; i++) {
+        int rc = retire_slot(ctx, ctx->slots[i]);
+        if (rc) return rc;
+    }
+    *samplenum = sn;
+    return DOPPLER_B200_OK;
+}
+
+int check_blocks(doppler_b200_ctx* ctx, size_t in_len, int intype, const float* shifts, size_t nblocks, size_t block_bytes,
+                 uint64_t* block_samples)
+{
+    if (!shifts || nblocks == 0) return fail(ctx, DOPPLER_B200_EINVAL, "no shift schedule");
+    const size_t ibps = bytes_per_sample(intype);
+    if (block_bytes == 0 || block_bytes % ibps != 0)
+        return fail(ctx, DOPPLER_B200_EINVAL, "block_bytes %zu is not a whole number of samples", block_bytes);
+    if ((in_len + block_bytes - 1) / block_bytes > nblocks)
+        return fail(ctx, DOPPLER_B200_EINVAL, "shift schedule has %zu blocks, input needs %zu", nblocks,
+                    (in_len + block_bytes - 1) / block_bytes);
+    *block_samples = block_bytes / ibps;
+    return DOPPLER_B200_OK;
+}
+
+}  // namespace
+
+// ===============================================================================================
+extern "C" {
+
+int doppler_b200_abi_version(void) { return DOPPLER_B200_ABI_VERSION; }
+
+int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
+{
+    if (!ctx_out) return DOPPLER_B200_EINVAL;
+    *ctx_out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, DOPPLER_B200_ENODEV, "no CUDA device: %s (this library has no CPU path)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, DOPPLER_B200_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+    cudaDeviceProp prop;
+    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, DOPPLER_B200_ENODEV, "device %d is sm_%d%d; this build carries sm_100a code only", device,
+                    prop.major, prop.minor);
+    CUDA_TRY(nullptr, cudaSetDevice(device));
+    doppler_b200_ctx* ctx = new (std::nothrow) doppler_b200_ctx;
+    if (!ctx) return fail(nullptr, DOPPLER_B200_ENOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->tables_ready, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e2 == cudaSuccess; i++)
+        for (int o = 0; o < 2 && e2 == cudaSuccess; o++) {
+            MixKernel k = mix_kernel_for(i, o);
+            e2 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((kSmemTabMaxEntries + dmix::kTabPad) * sizeof(float2)));
+            if (e2 == cudaSuccess)
+                e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[i][o], k, dmix::kThreads, 4096);
+        }
+    if (e2 != cudaSuccess) {
+        fail(nullptr, DOPPLER_B200_ECUDA, "context setup failed: %s", cudaGetErrorString(e2));
+        delete ctx;
+        return DOPPLER_B200_ECUDA;
+    }
+    *ctx_out = ctx;
+    return DOPPLER_B200_OK;
+}
+
+void doppler_b200_destroy(doppler_b200_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (Slot& sl : ctx->slots) {
+        if (sl.d_in) cudaFree(sl.d_in);
+        if (sl.d_out) cudaFree(sl.d_out);
+        if (sl.h_in) cudaFreeHost(sl.h_in);
+        if (sl.h_out) cudaFreeHost(sl.h_out);
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->tables_ready) cudaEventDestroy(ctx->tables_ready);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* doppler_b200_last_error(const doppler_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void* doppler_b200_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void doppler_b200_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+uint64_t doppler_b200_launch_count(const doppler_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int doppler_b200_synchronize(doppler_b200_ctx* ctx)
+{
+    if (!ctx) return DOPPLER_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DOPPLER_B200_OK;
+}
+
+// ---- fused path -------------------------------------------------------------------------------
+
+int doppler_b200_mix_dev(doppler_b200_ctx* ctx, const void* d_in, size_t in_len, int intype, int outtype, float shift_hz,
+                         uint32_t samplerate, uint32_t* samplenum, void* d_out, size_t out_cap, void* stream)
+{
+    uint64_t n = 0;
+    int rc = check_common(ctx, d_in, in_len, intype, outtype, samplenum, d_out, out_cap, &n);
+    if (rc) return rc;
+    if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail(ctx, DOPPLER_B200_EINVAL, "device buffers must be 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<dplan::Run> runs{dplan::Run{n, dplan::ratio(shift_hz, samplerate)}};
+    return launch_mix(ctx, d_in, d_out, n, intype, outtype, runs, samplenum, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int doppler_b200_mix_blocks_dev(doppler_b200_ctx* ctx, const void* d_in, size_t in_len, int intype, int outtype,
+                                const float* shifts, size_t nblocks, size_t block_bytes, uint32_t samplerate,
+                                uint32_t* samplenum, void* d_out, size_t out_cap, void* stream)
+{
+    uint64_t n = 0, bs = 0;
+    int rc = check_common(ctx, d_in, in_len, intype, outtype, samplenum, d_out, out_cap, &n);
+    if (rc) return rc;
+    if (n == 0) return DOPPLER_B200_OK;
+    rc = check_blocks(ctx, in_len, intype, shifts, nblocks, block_bytes, &bs);
+    if (rc) return rc;
+    if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail(ctx, DOPPLER_B200_EINVAL, "device buffers must be 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<dplan::Run> runs = dplan::runs_from_blocks(shifts, nblocks, bs, samplerate, n);
+    return launch_mix(ctx, d_in, d_out, n, intype, outtype, runs, samplenum, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int doppler_b200_mix(doppler_b200_ctx* ctx, const void* in, size_t in_len, int intype, int outtype, float shift_hz,
+                     uint32_t samplerate, uint32_t* samplenum, void* out, size_t out_cap, size_t* out_len)
+{
+    uint64_t n = 0;
+    int rc = check_common(ctx, in, in_len, intype, outtype, samplenum, out, out_cap, &n);
+    if (rc) return rc;
+    if (out_len) *out_len = 0;
+    if (n == 0) return DOPPLER_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    rc = mix_host(ctx, in, n, intype, outtype, &shift_hz, 1, 0, samplerate, samplenum, out);
+    if (rc == DOPPLER_B200_OK && out_len) *out_len = n * bytes_per_sample(outtype);
+    return rc;
+}
+
+int doppler_b200_mix_blocks(doppler_b200_ctx* ctx, const void* in, size_t in_len, int intype, int outtype,
+                            const float* shifts, size_t nblocks, size_t block_bytes, uint32_t samplerate,
+                            uint32_t* samplenum, void* out, size_t out_cap, size_t* out_len)
+{
+    uint64_t n = 0, bs = 0;
+    int rc = check_common(ctx, in, in_len, intype, outtype, samplenum, out, out_cap, &n);
+    if (rc) return rc;
+    if (out_len) *out_len = 0;
+    if (n == 0) return DOPPLER_B200_OK;
+    rc = check_blocks(ctx, in_len, intype, shifts, nblocks, block_bytes, &bs);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    rc = mix_host(ctx, in, n, intype, outtype, shifts, nblocks, bs, samplerate, samplenum, out);
+    if (rc == DOPPLER_B200_OK && out_len) *out_len = n * bytes_per_sample(outtype);
+    return rc;
+}
+
+// ---- the reference's three functions, one to one ---------------------------------------------
+
+int doppler_b200_shift_frequency(doppler_b200_ctx* ctx, const float* inbuf, size_t nsamples, uint32_t* samplenum,
+                                 float shift_hz, uint32_t samplerate, float* out)
+{
+    // Complex<f32> in, Complex<f32> out: the f32 ingest is a bit copy (dsp.rs:101-115) and the f32
+    // egress is a byte view (main.rs:89-93), so this IS the fused path with both types f32.
+    return doppler_b200_mix(ctx, inbuf, nsamples * 8, DOPPLER_B200_F32, DOPPLER_B200_F32, shift_hz, samplerate, samplenum,
+                            out, nsamples * 8, nullptr);
+}
+
+static int convert_host(doppler_b200_ctx* ctx, const uint8_t* inbuf, size_t len, int intype, float* out)
+{
+    if (!ctx) return DOPPLER_B200_EINVAL;
+    const size_t ibps = bytes_per_sample(intype);
+    if (len % ibps != 0)
+        return fail(ctx, DOPPLER_B200_EALIGN, "input length %zu is not a multiple of %zu (dsp.rs assert)", len, ibps);
+    const uint64_t n = len / ibps;
+    if (n == 0) return DOPPLER_B200_OK;
+    if (!inbuf || !out) return fail(ctx, DOPPLER_B200_EINVAL, "NULL buffer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t chunk = kHostChunkBytes / ibps;
+    for (uint64_t k = 0; k < n; k += chunk) {
+        const uint64_t m = std::min(chunk, n - k);
+        Slot& sl = ctx->slots[0];
+        int rc = ensure_slot(ctx, sl, std::min(chunk, n) * ibps, std::min(chunk, n) * 8);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(sl.d_in, inbuf + k * ibps, m * ibps, cudaMemcpyHostToDevice, sl.stream));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((m + dmix::kThreads - 1) / dmix::kThreads, (uint64_t)ctx->sm_count * 32);
+        if (intype == DOPPLER_B200_I16)
+            dmix::convert_kernel<0><<<grid, dmix::kThreads, 0, sl.stream>>>(sl.d_in, (float2*)sl.d_out, (uint32_t)m);
+        else
+            dmix::convert_kernel<1><<<grid, dmix::kThreads, 0, sl.stream>>>(sl.d_in, (float2*)sl.d_out, (uint32_t)m);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaMemcpyAsync(out + 2 * k, sl.d_out, m * 8, cudaMemcpyDeviceToHost, sl.stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(sl.stream));
+    }
+    return DOPPLER_B200_OK;
+}
+
+int doppler_b200_convert_iqi16_to_complex(doppler_b200_ctx* ctx, const uint8_t* inbuf, size_t len, float* out)
+{
+    return convert_host(ctx, inbuf, len, DOPPLER_B200_I16, out);
+}
+
+int doppler_b200_convert_iqf32_to_complex(doppler_b200_ctx* ctx, const uint8_t* inbuf, size_t len, float* out)
+{
+    return convert_host(ctx, inbuf, len, DOPPLER_B200_F32, out);
+}
+
+// ---- analytic samplenum (host only) -----------------------------------------------------------
+
+uint32_t doppler_b200_samplenum_advance(uint32_t samplenum, float shift_hz, uint32_t samplerate, uint64_t count)
+{
+    dplan::Planner pl;
+    std::vector<dplan::Run> runs{dplan::Run{count, dplan::ratio(shift_hz, samplerate)}};
+    return pl.advance(runs, samplenum);
+}
+
+uint32_t doppler_b200_samplenum_advance_blocks(uint32_t samplenum, const float* shifts, size_t nblocks, uint64_t block_samples,
+                                               uint32_t samplerate, uint64_t count)
+{
+    if (!shifts || nblocks == 0 || block_samples == 0) return samplenum;
+    dplan::Planner pl;
+    return pl.advance(dplan::runs_from_blocks(shifts, nblocks, block_samples, samplerate, count), samplenum);
+}
+
+long doppler_b200_plan_trace(uint32_t* samplenum, const float* shifts, size_t nblocks, uint64_t block_samples,
+                             uint32_t samplerate, uint64_t count, uint32_t* trace)
+{
+    if (!samplenum || !shifts || nblocks == 0 || block_samples == 0) return -1;
+    dplan::Planner pl;
+    std::vector<dplan::Piece> pieces;
+    pl.plan(dplan::runs_from_blocks(shifts, nblocks, block_samples, samplerate, count), 0, samplenum, &pieces);
+    if (trace) {
+        for (const dplan::Piece& p : pieces)
+            for (uint64_t k = p.k_begin; k < p.k_end; k++) {
+                const uint64_t off = k - p.k_begin;
+                trace[k] = p.period ? (uint32_t)(((uint64_t)p.base + off) % p.period) + 1u : p.base + (uint32_t)off;
+            }
+    }
+    return (long)pieces.size();
+}
+
+// ---- device self-test probes ------------------------------------------------------------------
+
+int doppler_b200_phasor_probe(doppler_b200_ctx* ctx, float r, uint32_t n0, size_t count, float* cos_out, float* sin_out)
+{
+    if (!ctx || !cos_out || !sin_out) return DOPPLER_B200_EINVAL;
+    if (count == 0) return DOPPLER_B200_OK;
+    if (count > (1u << 30)) return fail(ctx, DOPPLER_B200_EINVAL, "probe too large");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    float *dc = nullptr, *ds = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&dc, count * 4));
+    CUDA_TRY(ctx, cudaMalloc(&ds, count * 4));
+    dmix::phasor_probe_kernel<<<(uint32_t)((count + 255) / 256), 256, 0, ctx->stream>>>(r, n0, (uint32_t)count, dc, ds);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(cos_out, dc, count * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sin_out, ds, count * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dc);
+    cudaFree(ds);
+    if (e != cudaSuccess) return fail(ctx, DOPPLER_B200_ECUDA, "phasor probe: %s", cudaGetErrorString(e));
+    return DOPPLER_B200_OK;
+}
+
+int doppler_b200_sincosf_probe(doppler_b200_ctx* ctx, uint32_t first_bits, uint32_t stride, size_t count, float* sin_out,
+                               float* cos_out)
+{
+    if (!ctx || !cos_out || !sin_out) return DOPPLER_B200_EINVAL;
+    if (count == 0) return DOPPLER_B200_OK;
+    if (count > (1u << 30)) return fail(ctx, DOPPLER_B200_EINVAL, "probe too large");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    float *dc = nullptr, *ds = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&dc, count * 4));
+    CUDA_TRY(ctx, cudaMalloc(&ds, count * 4));
+    dmix::sincosf_probe_kernel<<<(uint32_t)((count + 255) / 256), 256, 0, ctx->stream>>>(first_bits, stride, (uint32_t)count, ds, dc);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(cos_out, dc, count * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sin_out, ds, count * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dc);
+    cudaFree(ds);
+    if (e != cudaSuccess) return fail(ctx, DOPPLER_B200_ECUDA, "sincosf probe: %s", cudaGetErrorString(e));
+    return DOPPLER_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+"""Python mirror of the reference's ``dsp`` module (/root/reference/src/dsp.rs) over the C ABI.
+
+Same names, same argument meaning, same failure behaviour (the reference's ``assert!`` panics
+become :class:`DopplerError` with ``code == EALIGN``).  ``samplenum`` -- a ``&mut u32`` in the
+reference (src/dsp.rs:117, state at src/main.rs:60) -- is passed in and returned.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+I16 = 0  # usage.rs:39-42 DataType::I16
+F32 = 1  # usage.rs:39-42 DataType::F32
+BUFFER_SIZE = 8192  # main.rs:49
+
+OK, EINVAL, EALIGN, ECAP, ECUDA, ENODEV, ENOMEM = range(7)
+_BPS = {I16: 4, F32: 8}
+
+
+class DopplerError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"doppler_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a.size else ctypes.c_void_p(0)
+
+
+def _as_bytes_array(buf):
+    a = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf.view(np.uint8).reshape(-1)
+    return np.ascontiguousarray(a)
+
+
+class Mixer:
+    """One context per GPU (include/doppler_b200.h: doppler_b200_create)."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        self._ctx = ctypes.c_void_p()
+        rc = self._lib.doppler_b200_create(int(device), ctypes.byref(self._ctx))
+        if rc != OK:
+            raise DopplerError(rc, self._lib.doppler_b200_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.doppler_b200_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise DopplerError(rc, self._lib.doppler_b200_last_error(self._ctx).decode())
+
+    @property
+    def launch_count(self):
+        return int(self._lib.doppler_b200_launch_count(self._ctx))
+
+    def synchronize(self):
+        self._check(self._lib.doppler_b200_synchronize(self._ctx))
+
+    # -- reference functions -------------------------------------------------------------
+    def convert_iqi16_to_complex(self, inbuf):
+        """dsp.rs:85-99."""
+        a = _as_bytes_array(inbuf)
+        out = np.empty(a.size // 4, dtype=np.complex64)
+        self._check(self._lib.doppler_b200_convert_iqi16_to_complex(self._ctx, _ptr(a), a.size, _ptr(out)))
+        return out
+
+    def convert_iqf32_to_complex(self, inbuf):
+        """dsp.rs:101-115."""
+        a = _as_bytes_array(inbuf)
+        out = np.empty(a.size // 8, dtype=np.complex64)
+        self._check(self._lib.doppler_b200_convert_iqf32_to_complex(self._ctx, _ptr(a), a.size, _ptr(out)))
+        return out
+
+    def shift_frequency(self, inbuf, samplenum, shift_hz, samplerate):
+        """dsp.rs:117-134.  Returns (output complex64 array, new samplenum)."""
+        a = np.ascontiguousarray(inbuf, dtype=np.complex64)
+        out = np.empty_like(a)
+        sn = ctypes.c_uint32(samplenum)
+        self._check(self._lib.doppler_b200_shift_frequency(self._ctx, _ptr(a), a.size, ctypes.byref(sn),
+                                                           ctypes.c_float(shift_hz), int(samplerate), _ptr(out)))
+        return out, sn.value
+
+    # -- fused path ----------------------------------------------------------------------
+    def mix(self, inbuf, intype, outtype, shift_hz, samplerate, samplenum=0):
+        """convert -> shift_frequency -> egress (main.rs:65-94) in one pass.  Returns (bytes array, samplenum)."""
+        a = _as_bytes_array(inbuf)
+        out = np.empty((a.size // _BPS[intype]) * _BPS[outtype], dtype=np.uint8)
+        sn = ctypes.c_uint32(samplenum)
+        n = ctypes.c_size_t(0)
+        self._check(self._lib.doppler_b200_mix(self._ctx, _ptr(a), a.size, intype, outtype, ctypes.c_float(shift_hz),
+                                               int(samplerate), ctypes.byref(sn), _ptr(out), out.size, ctypes.byref(n)))
+        return out[:n.value], sn.value
+
+    def mix_blocks(self, inbuf, intype, outtype, shifts_hz, samplerate, samplenum=0, block_bytes=BUFFER_SIZE):
+        """One shift per `block_bytes` of input (track mode, main.rs:177)."""
+        a = _as_bytes_array(inbuf)
+        sh = np.ascontiguousarray(shifts_hz, dtype=np.float32)
+        out = np.empty((a.size // _BPS[intype]) * _BPS[outtype], dtype=np.uint8)
+        sn = ctypes.c_uint32(samplenum)
+        n = ctypes.c_size_t(0)
+        self._check(self._lib.doppler_b200_mix_blocks(self._ctx, _ptr(a), a.size, intype, outtype, _ptr(sh), sh.size,
+                                                      block_bytes, int(samplerate), ctypes.byref(sn), _ptr(out),
+                                                      out.size, ctypes.byref(n)))
+        return out[:n.value], sn.value
+
+    # -- device-resident (raw pointers; used by bench.py with torch tensors) -------------
+    def mix_dev(self, d_in, in_len, intype, outtype, shift_hz, samplerate, samplenum, d_out, out_cap, stream=None):
+        sn = ctypes.c_uint32(samplenum)
+        self._check(self._lib.doppler_b200_mix_dev(self._ctx, ctypes.c_void_p(d_in), in_len, intype, outtype,
+                                                   ctypes.c_float(shift_hz), int(samplerate), ctypes.byref(sn),
+                                                   ctypes.c_void_p(d_out), out_cap, ctypes.c_void_p(stream or 0)))
+        return sn.value
+
+    def mix_blocks_dev(self, d_in, in_len, intype, outtype, shifts_hz, samplerate, samplenum, d_out, out_cap,
+                       block_bytes=BUFFER_SIZE, stream=None):
+        sh = np.ascontiguousarray(shifts_hz, dtype=np.float32)
+        sn = ctypes.c_uint32(samplenum)
+        self._check(self._lib.doppler_b200_mix_blocks_dev(self._ctx, ctypes.c_void_p(d_in), in_len, intype, outtype,
+                                                          _ptr(sh), sh.size, block_bytes, int(samplerate),
+                                                          ctypes.byref(sn), ctypes.c_void_p(d_out), out_cap,
+                                                          ctypes.c_void_p(stream or 0)))
+        return sn.value
+
+    # -- probes --------------------------------------------------------------------------
+    def phasor_probe(self, r, n0, count):
+        c = np.empty(count, dtype=np.float32)
+        s = np.empty(count, dtype=np.float32)
+        self._check(self._lib.doppler_b200_phasor_probe(self._ctx, ctypes.c_float(r), int(n0), count, _ptr(c), _ptr(s)))
+        return c, s
+
+    def sincosf_probe(self, first_bits, stride, count):
+        s = np.empty(count, dtype=np.float32)
+        c = np.empty(count, dtype=np.float32)
+        self._check(self._lib.doppler_b200_sincosf_probe(self._ctx, int(first_bits), int(stride), count, _ptr(s), _ptr(c)))
+        return s, c
+
+
+# ---- host-only analytic samplenum (no GPU needed) ------------------------------------------
+
+def samplenum_advance(samplenum, shift_hz, samplerate, count):
+    return int(_lib.load().doppler_b200_samplenum_advance(int(samplenum), ctypes.c_float(shift_hz), int(samplerate), int(count)))
+
+
+def samplenum_advance_blocks(samplenum, shifts_hz, block_samples, samplerate, count):
+    sh = np.ascontiguousarray(shifts_hz, dtype=np.float32)
+    return int(_lib.load().doppler_b200_samplenum_advance_blocks(int(samplenum), _ptr(sh), sh.size, int(block_samples),
+                                                                 int(samplerate), int(count)))
+
+
+def plan_trace(samplenum, shifts_hz, block_samples, samplerate, count):
+    """(per-sample samplenum sequence, final samplenum, number of closed-form pieces)."""
+    sh = np.ascontiguousarray(shifts_hz, dtype=np.float32)
+    trace = np.empty(count, dtype=np.uint32)
+    sn = ctypes.c_uint32(samplenum)
+    npieces = _lib.load().doppler_b200_plan_trace(ctypes.byref(sn), _ptr(sh), sh.size, int(block_samples), int(samplerate),
+                                                  int(count), _ptr(trace))
+    if npieces < 0:
+        raise DopplerError(EINVAL, "bad plan_trace arguments")
+    return trace, sn.value, int(npieces)
+
+
+# ---- module-level functions with the reference's names (default context on cuda:0) ---------
+_default = None
+
+
+def _ctx():
+    global _default
+    if _default is None:
+        _default = Mixer(0)
+    return _default
+
+
+def convert_iqi16_to_complex(inbuf):
+    return _ctx().convert_iqi16_to_complex(inbuf)
+
+
+def convert_iqf32_to_complex(inbuf):
+    return _ctx().convert_iqf32_to_complex(inbuf)
+
+
+def shift_frequency(inbuf, samplenum, shift_hz, samplerate):
+    return _ctx().shift_frequency(inbuf, samplenum, shift_hz, samplerate)

@@ -1,0 +1,59 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run by `pytest -m gpu` on the GPU box)")
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_built():
+    """Build the oracle, the host check twin and the product library if they are missing.
+    (On the GPU box the prebuilt in-tree .so files travel with the snapshot.)"""
+    need = [
+        os.path.join(ROOT, "oracle", "liboracle.so"),
+        os.path.join(ROOT, "tests", "native", "libhostcheck.so"),
+        os.path.join(ROOT, "doppler_b200", "libdoppler_b200.so"),
+    ]
+    if not all(os.path.exists(p) for p in need):
+        import __graft_entry__
+        __graft_entry__.build()
+    yield
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from tests import oracle_lib
+    return oracle_lib.Oracle()
+
+
+@pytest.fixture(scope="session")
+def mixer():
+    import doppler_b200
+    m = doppler_b200.Mixer(0)
+    yield m
+    m.close()
