@@ -1,0 +1,216 @@
+"""Parity of the sm_100a mixer (through the C ABI) with the CPU oracle: bit-exact bytes for i16
+output, bit-exact floats for f32 output (NaN payloads aside).  Runs on the GPU box only.
+
+The oracle is the restatement in oracle/ calling the reference's own compiled complex.c when
+oracle/_ref is present (built in the authoring container, shipped with the snapshot)."""
+import numpy as np
+import pytest
+
+import doppler_b200
+from doppler_b200 import F32, I16
+from tests.oracle_lib import BUFFER_SIZE, same_bits_f32
+
+pytestmark = pytest.mark.gpu
+
+BPS = {I16: 4, F32: 8}
+
+
+def make_input(rng, n, typ, kind="uniform"):
+    if typ == I16:
+        if kind == "fullscale":
+            v = rng.choice(np.array([-32768, -32767, 32767, 23170, -23170, 0, 1, -1], dtype=np.int16), 2 * n)
+        else:
+            v = rng.integers(-32768, 32768, 2 * n, dtype=np.int32).astype(np.int16)
+        return v.view(np.uint8)
+    v = rng.uniform(-0.7, 0.7, 2 * n).astype(np.float32)
+    if kind == "fullscale":
+        v = rng.choice(np.array([1.0, -1.0, 0.70710678, -0.70710678, 1.5, -2.0, 0.0, -0.0], dtype=np.float32), 2 * n)
+    return v.view(np.uint8)
+
+
+def check(oracle, got, want, outtype):
+    assert got.size == want.size
+    if outtype == I16:
+        if not np.array_equal(got, want):
+            g, w = got.view("<i2"), want.view("<i2")
+            bad = np.flatnonzero(g != w)
+            raise AssertionError(f"{bad.size} of {g.size} i16 values differ; first at {bad[0]}: got {g[bad[0]]} want {w[bad[0]]}")
+    else:
+        if not same_bits_f32(got, want):
+            g, w = got.view(np.uint32), want.view(np.uint32)
+            bad = np.flatnonzero(g != w)
+            raise AssertionError(f"{bad.size} of {g.size} f32 words differ; first at {bad[0]}: got {g[bad[0]]:08x} want {w[bad[0]]:08x}")
+
+
+TYPE_PAIRS = [(I16, I16), (I16, F32), (F32, I16), (F32, F32)]
+# (shift, fs): table-in-shared-memory periods, an L2-sized table, direct evaluation, degenerate ratios
+SHIFTS = [(-15000.0, 256000), (100000.0, 10_000_000), (815000.0, 2_400_000), (-9876.54, 1_024_000),
+          (7321.7, 1_024_000), (0.0, 48000), (48000.0, 48000), (1.0, 2_000_000_000)]
+
+
+@pytest.mark.parametrize("intype,outtype", TYPE_PAIRS)
+@pytest.mark.parametrize("shift,fs", SHIFTS)
+def test_mix_matches_oracle(oracle, mixer, intype, outtype, shift, fs):
+    rng = np.random.default_rng(hash((intype, outtype, fs)) & 0xFFFF)
+    for n in (1, 3, 2047, 4096, 4097, 70_001, 400_003):
+        buf = make_input(rng, n, intype)
+        got, sn = mixer.mix(buf, intype, outtype, shift, fs)
+        want, sn_ref = oracle.mix(buf, intype, outtype, shift, fs)
+        assert sn == sn_ref
+        check(oracle, got, want, outtype)
+
+
+@pytest.mark.parametrize("intype,outtype", TYPE_PAIRS)
+def test_empty_and_misaligned_inputs(oracle, mixer, intype, outtype):
+    got, sn = mixer.mix(np.zeros(0, dtype=np.uint8), intype, outtype, 1000.0, 48000, samplenum=17)
+    assert got.size == 0 and sn == 17
+    with pytest.raises(doppler_b200.DopplerError) as ei:  # the reference's assert!, dsp.rs:87,103
+        mixer.mix(np.zeros(BPS[intype] * 5 + 2, dtype=np.uint8), intype, outtype, 1000.0, 48000)
+    assert ei.value.code == doppler_b200.dsp.EALIGN
+
+
+@pytest.mark.parametrize("intype,outtype", TYPE_PAIRS)
+def test_fullscale_saturation(oracle, mixer, intype, outtype):
+    """(1+1j)*e^{j theta} exceeds i16 range: Rust's saturating `as i16` (main.rs:77-78)."""
+    rng = np.random.default_rng(99)
+    buf = make_input(rng, 50_000, intype, "fullscale")
+    got, _ = mixer.mix(buf, intype, outtype, 815000.0, 2_400_000)
+    want, _ = oracle.mix(buf, intype, outtype, 815000.0, 2_400_000)
+    check(oracle, got, want, outtype)
+
+
+def test_f32_specials_pass_through(oracle, mixer):
+    """NaN / Inf / denormal inputs (the f32 ingest is a bit copy, dsp.rs:101-115)."""
+    pat = np.array([0x7FC00000, 0x3F800000, 0x7F800000, 0x00000000, 0xFF800000, 0x3F000000, 0x00000001, 0x80000001,
+                    0x00800000, 0x7F7FFFFF, 0x3F800000, 0x7F7FFFFF], dtype=np.uint32)
+    buf = np.tile(pat, 1000).view(np.uint8)
+    for outtype in (I16, F32):
+        got, _ = mixer.mix(buf, F32, outtype, 100000.0, 10_000_000)
+        want, _ = oracle.mix(buf, F32, outtype, 100000.0, 10_000_000)
+        check(oracle, got, want, outtype)
+
+
+def test_samplenum_carried_across_calls(oracle, mixer):
+    """Library callers pump block after block carrying samplenum (main.rs:60): chunked == whole."""
+    rng = np.random.default_rng(4)
+    n = 300_000
+    buf = make_input(rng, n, I16)
+    for shift, fs in [(-15000.0, 256000), (-9876.54, 1_024_000)]:
+        want, sn_ref = oracle.mix(buf, I16, I16, shift, fs)
+        sn = 0
+        parts = []
+        k = 0
+        for m in (2048, 2048, 1, 99_999, 4096, n):  # last one clipped
+            m = min(m, n - k)
+            out, sn = mixer.mix(buf[4 * k:4 * (k + m)], I16, I16, shift, fs, samplenum=sn)
+            parts.append(out)
+            k += m
+        assert k == n and sn == sn_ref
+        check(oracle, np.concatenate(parts), want, I16)
+
+
+def test_reference_named_functions(oracle, mixer):
+    """dsp::convert_iqi16_to_complex / convert_iqf32_to_complex / shift_frequency one to one."""
+    rng = np.random.default_rng(11)
+    raw = rng.integers(-32768, 32768, 2 * 10_001, dtype=np.int32).astype("<i2")
+    assert np.array_equal(mixer.convert_iqi16_to_complex(raw.tobytes()).view(np.uint32),
+                          oracle.convert_iqi16_to_complex(raw.tobytes()).view(np.uint32))
+    f = rng.uniform(-2, 2, 2 * 9_999).astype("<f4")
+    f[:4] = [np.nan, np.inf, -0.0, 1e-42]
+    assert np.array_equal(mixer.convert_iqf32_to_complex(f.tobytes()).view(np.uint32),
+                          oracle.convert_iqf32_to_complex(f.tobytes()).view(np.uint32))
+    with pytest.raises(doppler_b200.DopplerError):
+        mixer.convert_iqi16_to_complex(b"\0" * 6)
+    x = (rng.uniform(-1, 1, 125_000) + 1j * rng.uniform(-1, 1, 125_000)).astype(np.complex64)
+    sn_g = sn_o = 0
+    for _ in range(3):  # test_bench_shift_frequency's shape: 125 000 samples, 815 kHz @ 2.4 Msps (dsp.rs:136-157)
+        got, sn_g = mixer.shift_frequency(x, sn_g, 815000.0, 2_400_000)
+        want, sn_o = oracle.shift_frequency(x, sn_o, 815000.0, 2_400_000)
+        assert sn_g == sn_o
+        assert same_bits_f32(got.view(np.uint8), want.view(np.uint8))
+
+
+@pytest.mark.parametrize("intype,outtype", TYPE_PAIRS)
+def test_block_schedule_track_mode(oracle, mixer, intype, outtype):
+    """One shift per 8192-byte block, samplenum carried across shift changes (main.rs:177)."""
+    rng = np.random.default_rng(21)
+    fs = 1_024_000
+    shifts = np.concatenate([np.repeat(np.float32(-9876.54), 60), np.repeat(np.float32(-9871.02), 55),
+                             rng.uniform(-12000, 12000, 17).astype(np.float32), np.repeat(np.float32(5000.0), 40)])
+    nbytes = shifts.size * BUFFER_SIZE - BPS[intype] * 333  # short last block
+    buf = make_input(rng, nbytes // BPS[intype], intype)
+    got, sn = mixer.mix_blocks(buf, intype, outtype, shifts, fs)
+    want, sn_ref = oracle.mix_blocks(buf, intype, outtype, shifts, fs)
+    assert sn == sn_ref
+    check(oracle, got, want, outtype)
+
+
+def test_track_replay_overpass(oracle, mixer):
+    """cfg3 (cut): analytic overpass Doppler table -> the reference's replay driver (oracle) gives
+    bytes + the per-block shift schedule; the planned entry point must reproduce the bytes."""
+    fs = 1_024_000
+    secs = 6
+    t = np.arange(secs + 2, dtype=np.float64)
+    v, d, tc, ftx = 7500.0, 700e3, 3.0, 437_505_000.0
+    rr_km_s = v * v * (t - tc) / np.sqrt(d * d + (v * (t - tc)) ** 2) / 1000.0
+    table = np.array([oracle.doppler_hz(x, 437_505_000) for x in rr_km_s])
+    rng = np.random.default_rng(1024000)
+    n = secs * fs
+    tt = np.arange(n)
+    sig = 0.25 * np.exp(2j * np.pi * 15000.0 / fs * tt) + 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    iq = np.empty(2 * n, dtype=np.int16)
+    iq[0::2] = np.clip(np.round(sig.real * 32767), -32768, 32767)
+    iq[1::2] = np.clip(np.round(sig.imag * 32767), -32768, 32767)
+    want, sn_ref, shifts, panicked = oracle.track_replay_stream(iq.view(np.uint8), I16, I16, table, 5000, fs)
+    assert not panicked
+    got, sn = mixer.mix_blocks(iq.view(np.uint8), I16, I16, shifts, fs)
+    assert sn == sn_ref
+    check(oracle, got, want, I16)
+
+
+def test_large_period_l2_table_and_direct_paths_agree(oracle, mixer):
+    """Same stream through (a) one call long enough to build a table and (b) many short calls that
+    evaluate sincosf directly must give identical bytes (tables are built by the same routine)."""
+    rng = np.random.default_rng(8)
+    n = 600_000
+    buf = make_input(rng, n, F32)
+    shift, fs = -9876.54, 1_024_000  # period 111 145
+    whole, sn_w = mixer.mix(buf, F32, F32, shift, fs)
+    m2 = doppler_b200.Mixer(0)  # fresh context: no cached table
+    sn = 0
+    parts = []
+    for k in range(0, n, 50_000):
+        out, sn = m2.mix(buf[8 * k:8 * (k + 50_000)], F32, F32, shift, fs, samplenum=sn)
+        parts.append(out)
+    m2.close()
+    assert sn == sn_w
+    assert same_bits_f32(np.concatenate(parts), whole)
+    want, _ = oracle.mix(buf, F32, F32, shift, fs)
+    check(oracle, whole, want, F32)
+
+
+def test_device_sincosf_matches_host_libm(oracle, mixer):
+    """The kernel's sincosf against this box's libm over a strided sweep of all float bit patterns
+    plus dense windows at the branch points."""
+    for first, stride, count in [(0, 4099, 2**32 // 4099), (0x3F490FDB - 50_000, 1, 100_000), (0x42F00000 - 50_000, 1, 100_000),
+                                 (0xBF490FDB - 50_000, 1, 100_000), (0xC2F00000 - 50_000, 1, 100_000), (0x7F7F0000, 1, 70_000),
+                                 (0x39800000 - 50_000, 1, 100_000)]:
+        s, c = mixer.sincosf_probe(first, stride, count)
+        bits = (np.uint64(first) + np.arange(count, dtype=np.uint64) * np.uint64(stride)).astype(np.uint32)
+        s_ref, c_ref = oracle.sincosf_batch(bits.view(np.float32))
+        assert same_bits_f32(s, s_ref) and same_bits_f32(c, c_ref)
+
+
+@pytest.mark.parametrize("shift,fs,n0,count", [(-15000.0, 256000, 0, 1000), (7321.7, 1_024_000, 0, 120_000),
+                                               (4_000_000.5, 200_000_000, 1, 1_000_000), (-9876.54, 1_024_000, 2**24 - 1000, 5000),
+                                               (1.0, 2_000_000_000, 2**32 - 2000, 4000)])
+def test_device_phasor_matches_reference_ccexpf(oracle, mixer, shift, fs, n0, count):
+    """(cos, sin) of theta_f32(n) as the reference forms it (dsp.rs:121-122)."""
+    r = np.float32(shift) / np.float32(fs)
+    c, s = mixer.phasor_probe(float(r), n0, count)
+    n = (np.uint64(n0) + np.arange(count, dtype=np.uint64)).astype(np.uint32)
+    theta = (np.float32(-2.0) * np.float32(np.pi)) * (r * n.astype(np.float32))
+    s_ref, c_ref = oracle.sincosf_batch(theta)
+    assert same_bits_f32(s, s_ref) and same_bits_f32(c, c_ref)
+    re, im = oracle.ccexpf(0.0, float(theta[count // 2]))
+    assert np.float32(re).tobytes() == c[count // 2].tobytes() and np.float32(im).tobytes() == s[count // 2].tobytes()
