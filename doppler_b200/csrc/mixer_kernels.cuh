@@ -30,8 +30,8 @@
 
 namespace dmix {
 
-constexpr int kThreads = 256;
-constexpr int kUnroll = 4;
+constexpr int kThreads = 256;   // default CTA size (table builder, converters, default mixer config)
+constexpr int kUnroll = 4;      // default groups per thread per tile
 constexpr uint32_t kNoTab = 0xffffffffu;
 constexpr int kInlinePieces = 4;
 constexpr int kTabPad = 4;   // table entries replicated past the period (>= max group size)
@@ -41,9 +41,9 @@ constexpr int F32 = 1;
 
 // samples per thread-group: the side with the wider sample gets 16 bytes per lane
 __host__ __device__ constexpr int group_samples(int in, int out) { return (in == I16 && out == I16) ? 4 : 2; }
-__host__ __device__ constexpr uint32_t tile_samples(int in, int out)
+__host__ __device__ constexpr uint32_t tile_samples(int in, int out, int threads = kThreads, int unroll = kUnroll)
 {
-    return (uint32_t)kThreads * kUnroll * group_samples(in, out);
+    return (uint32_t)threads * unroll * group_samples(in, out);
 }
 
 struct DevPiece {          // launch-relative sample indices
@@ -55,7 +55,7 @@ struct DevPiece {          // launch-relative sample indices
     uint32_t tab;          // first entry of this piece's phasor table in the arena, or kNoTab
     uint32_t magic;        // division by `period`: q = (x * magic) >> shift for x < 2^31
     uint32_t shift;
-    uint32_t step_u;       // (kThreads * G) mod period
+    uint32_t step_u;       // (CTA threads * G) mod period
     uint32_t pad[3];
 };
 static_assert(sizeof(DevPiece) == 48, "DevPiece layout");
@@ -70,6 +70,7 @@ struct MixArgs {
     uint32_t ntiles;
     uint32_t tiles_per_cta;
     uint32_t smem_entries;    // capacity of the shared-memory table (excluding pad)
+    uint32_t interleave;      // 0: CTA b owns tiles [b*tiles_per_cta, (b+1)*tiles_per_cta); 1: tiles b, b+grid, ...
     DevPiece inl[kInlinePieces];
 };
 
@@ -210,22 +211,22 @@ __device__ __forceinline__ uint32_t piece_samplenum(const DevPiece& p, uint32_t 
 
 enum FastMode { kTabShared = 0, kTabGlobal = 1, kDirectPeriodic = 2, kDirectLinear = 3 };
 
-// A full tile inside one piece.  All kUnroll group loads are issued before any arithmetic.
-template <int IN, int OUT, int MODE>
+// A full tile inside one piece.  All U group loads are issued before any arithmetic.
+template <int IN, int OUT, int MODE, int T, int U>
 __device__ __forceinline__ void fast_tile(const MixArgs& a, const DevPiece& p, uint32_t k0, const float2* tab)
 {
     constexpr int G = group_samples(IN, OUT);
     const uint32_t g0 = k0 / G + threadIdx.x;
-    float2 smp[kUnroll][G];
+    float2 smp[U][G];
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++) load_group<IN, G>(a.in, g0 + u * kThreads, smp[u]);
+    for (int u = 0; u < U; u++) load_group<IN, G>(a.in, g0 + u * T, smp[u]);
 
     const uint32_t off = (k0 - p.k_begin) + threadIdx.x * G;
     uint32_t j = 0;
     if constexpr (MODE != kDirectLinear) j = piece_samplenum(p, off) - 1u;   // phase index in [0, period)
 
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++) {
+    for (int u = 0; u < U; u++) {
         float2 res[G];
 #pragma unroll
         for (int s = 0; s < G; s++) {
@@ -239,11 +240,11 @@ __device__ __forceinline__ void fast_tile(const MixArgs& a, const DevPiece& p, u
                 if (n > p.period) n -= p.period;
                 ph = phasor(p.r, n);
             } else {
-                ph = phasor(p.r, p.base + off + (uint32_t)(u * kThreads * G + s));
+                ph = phasor(p.r, p.base + off + (uint32_t)(u * T * G + s));
             }
             res[s] = cmul_unfused(smp[u][s], ph);
         }
-        store_group<OUT, G>(a.out, g0 + u * kThreads, res);
+        store_group<OUT, G>(a.out, g0 + u * T, res);
         if constexpr (MODE != kDirectLinear) {
             j += p.step_u;
             if (j >= p.period) j -= p.period;
@@ -252,12 +253,12 @@ __device__ __forceinline__ void fast_tile(const MixArgs& a, const DevPiece& p, u
 }
 
 // Generic per-sample tile: piece boundaries inside the tile and/or the ragged end of the buffer.
-template <int IN, int OUT>
+template <int IN, int OUT, int T, int U>
 __device__ __noinline__ void slow_tile(const MixArgs& a, uint32_t pi, uint32_t k0)
 {
-    constexpr uint32_t kTile = tile_samples(IN, OUT);
+    constexpr uint32_t kTile = tile_samples(IN, OUT, T, U);
     DevPiece p = get_piece(a, pi);
-    for (uint32_t i = threadIdx.x; i < kTile; i += kThreads) {
+    for (uint32_t i = threadIdx.x; i < kTile; i += T) {
         const uint32_t k = k0 + i;
         if (k >= a.nsamples) break;
         if (k >= p.k_end) {
@@ -270,19 +271,28 @@ __device__ __noinline__ void slow_tile(const MixArgs& a, uint32_t pi, uint32_t k
     }
 }
 
-template <int IN, int OUT>
-__global__ void __launch_bounds__(kThreads) mix_kernel(const __grid_constant__ MixArgs a)
+// T threads per CTA, U groups per thread per tile, at least MINB resident CTAs per SM.
+template <int IN, int OUT, int T = kThreads, int U = kUnroll, int MINB = 0>
+__global__ void __launch_bounds__(T, MINB) mix_kernel(const __grid_constant__ MixArgs a)
 {
-    constexpr uint32_t kTile = tile_samples(IN, OUT);
+    constexpr uint32_t kTile = tile_samples(IN, OUT, T, U);
     extern __shared__ float2 tab_s[];
 
-    uint32_t tile = blockIdx.x * a.tiles_per_cta;
-    const uint32_t tile_end = min(tile + a.tiles_per_cta, a.ntiles);
+    uint32_t tile, tile_end, tile_step;
+    if (a.interleave) {
+        tile = blockIdx.x;
+        tile_end = a.ntiles;
+        tile_step = gridDim.x;
+    } else {
+        tile = blockIdx.x * a.tiles_per_cta;
+        tile_end = min(tile + a.tiles_per_cta, a.ntiles);
+        tile_step = 1;
+    }
     uint32_t pi = 0;
     uint32_t staged = 0xffffffffu;   // piece whose table is in shared memory
     DevPiece p = get_piece(a, 0);
 
-    for (; tile < tile_end; ++tile) {
+    for (; tile < tile_end; tile += tile_step) {
         const uint32_t k0 = tile * kTile;
         if (k0 >= p.k_end) {
             pi = find_piece(a, pi, k0);
@@ -290,24 +300,24 @@ __global__ void __launch_bounds__(kThreads) mix_kernel(const __grid_constant__ M
         }
         const bool fast = (k0 + kTile <= p.k_end) && (k0 + kTile <= a.nsamples);
         if (!fast) {
-            slow_tile<IN, OUT>(a, pi, k0);
+            slow_tile<IN, OUT, T, U>(a, pi, k0);
             continue;
         }
         if (p.period == 0) {
-            fast_tile<IN, OUT, kDirectLinear>(a, p, k0, nullptr);
+            fast_tile<IN, OUT, kDirectLinear, T, U>(a, p, k0, nullptr);
         } else if (p.tab == kNoTab) {
-            fast_tile<IN, OUT, kDirectPeriodic>(a, p, k0, nullptr);
+            fast_tile<IN, OUT, kDirectPeriodic, T, U>(a, p, k0, nullptr);
         } else if (p.period <= a.smem_entries) {
             if (staged != pi) {            // CTA-uniform
                 __syncthreads();
-                for (uint32_t e = threadIdx.x; e < p.period + kTabPad; e += kThreads)
+                for (uint32_t e = threadIdx.x; e < p.period + kTabPad; e += T)
                     tab_s[e] = __ldg(a.tables + p.tab + e);
                 __syncthreads();
                 staged = pi;
             }
-            fast_tile<IN, OUT, kTabShared>(a, p, k0, tab_s);
+            fast_tile<IN, OUT, kTabShared, T, U>(a, p, k0, tab_s);
         } else {
-            fast_tile<IN, OUT, kTabGlobal>(a, p, k0, a.tables + p.tab);
+            fast_tile<IN, OUT, kTabGlobal, T, U>(a, p, k0, a.tables + p.tab);
         }
     }
 }
