@@ -250,7 +250,7 @@ def main():
     # one mixer launch per step on this rank (the phasor table is built once, in warm-up)
     achieved = BYTES_PER_SAMPLE * n / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "dmix::mix_kernel<F32,I16>", "bytes_per_sample": BYTES_PER_SAMPLE,
+                "peak_source": peak_src, "kernel": "dmix::mix_stream_kernel<F32,I16,...> (per-warp cp.async.bulk pipelines)", "bytes_per_sample": BYTES_PER_SAMPLE,
                 "note": "per-GPU; time = CUDA events on the launch stream over the timed region / launches"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):

@@ -39,6 +39,21 @@ SIGNATURES = {
     "doppler_b200_samplenum_advance": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_float, ctypes.c_uint32, ctypes.c_uint64]),
     "doppler_b200_samplenum_advance_blocks": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
                                                                 ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64]),
+    "doppler_b200_doppler_hz": (ctypes.c_double, [ctypes.c_double, ctypes.c_uint32]),
+    "doppler_b200_track_shift": (ctypes.c_float, [ctypes.c_double, ctypes.c_int32]),
+    "doppler_b200_replay_seconds": (ctypes.c_int64, [ctypes.c_uint64, ctypes.c_uint32]),
+    "doppler_b200_replay_schedule": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_uint32, ctypes.c_int,
+                                                       ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]),
+    "doppler_b200_tracker_create": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                                    ctypes.POINTER(ctypes.c_void_p)]),
+    "doppler_b200_tracker_create_from_lines": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_double,
+                                                               ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_void_p)]),
+    "doppler_b200_tracker_destroy": (None, [ctypes.c_void_p]),
+    "doppler_b200_tracker_last_error": (ctypes.c_char_p, []),
+    "doppler_b200_tracker_observe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double] + [ctypes.POINTER(ctypes.c_double)] * 4),
+    "doppler_b200_tracker_teme": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "doppler_b200_tracker_doppler_table": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_double, ctypes.c_uint32, ctypes.c_size_t,
+                                                             ctypes.c_void_p]),
     "doppler_b200_plan_trace": (ctypes.c_long, [u32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32,
                                                 ctypes.c_uint64, ctypes.c_void_p]),
     "doppler_b200_phasor_probe": (ctypes.c_int, [c_ctx, ctypes.c_float, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_void_p,

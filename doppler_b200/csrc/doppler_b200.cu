@@ -67,7 +67,6 @@ struct doppler_b200_ctx {
     Slot slots[kSlots];
     std::string err;
     uint64_t launches = 0;
-    int occ[2][2] = {{0, 0}, {0, 0}};   // resident CTAs per SM per (in, out) variant
 };
 
 namespace {
@@ -99,10 +98,31 @@ inline bool valid_type(int t) { return t == DOPPLER_B200_I16 || t == DOPPLER_B20
 
 using MixKernel = void (*)(const MixArgs);
 
-MixKernel mix_kernel_for(int in, int out)
+// The streaming kernel's shape per (intype, outtype): WARPS pipelines per CTA, S stages, U rows
+// per tile -- chosen on B200 with tools/tune (profiles/r01_tune_stream.md).
+struct StreamShape {
+    MixKernel kern;
+    int warps;
+    uint32_t tile_samples, row_samples;
+    uint32_t fixed_smem;
+    uint32_t (*table_bytes)(uint32_t period);
+};
+
+template <int IN, int OUT, int WARPS, int S, int U>
+StreamShape make_shape()
 {
-    if (in == DOPPLER_B200_I16) return out == DOPPLER_B200_I16 ? dmix::mix_kernel<0, 0> : dmix::mix_kernel<0, 1>;
-    return out == DOPPLER_B200_I16 ? dmix::mix_kernel<1, 0> : dmix::mix_kernel<1, 1>;
+    using C = dmix::StreamCfg<IN, OUT, WARPS, S, U>;
+    return StreamShape{dmix::mix_stream_kernel<IN, OUT, WARPS, S, U>, WARPS, (uint32_t)C::kTileSamples, (uint32_t)C::kRow,
+                       (uint32_t)C::kFixedSmem, &C::table_bytes};
+}
+
+const StreamShape& shape_for(int in, int out)
+{
+    static const StreamShape shapes[2][2] = {
+        {make_shape<0, 0, 20, 2, 2>(), make_shape<0, 1, 20, 3, 2>()},
+        {make_shape<1, 0, 16, 2, 3>(), make_shape<1, 1, 16, 2, 2>()},
+    };
+    return shapes[in][out];
 }
 
 // floor-division constants for x < 2^31 (Granlund-Montgomery round-up method, N = 31)
@@ -166,18 +186,18 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
     std::vector<dplan::Piece> pieces;
     ctx->planner.plan(runs, 0, samplenum, &pieces);
 
-    const int G = dmix::group_samples(intype, outtype);
-    const uint32_t tile = dmix::tile_samples(intype, outtype);
+    const StreamShape& shape = shape_for(intype, outtype);
     const size_t ibps = bytes_per_sample(intype), obps = bytes_per_sample(outtype);
-    MixKernel kern = mix_kernel_for(intype, outtype);
+    // launches are cut at tile boundaries so that every launch but the last has no ragged tail
+    const uint64_t launch_max = kLaunchMaxSamples / shape.tile_samples * shape.tile_samples;
 
     if (ctx->tables_event_valid) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->tables_ready, 0));
 
     size_t first_piece = 0;
-    for (uint64_t l0 = 0; l0 < nsamples; l0 += kLaunchMaxSamples) {
-        const uint64_t l1 = std::min(nsamples, l0 + kLaunchMaxSamples);
+    for (uint64_t l0 = 0; l0 < nsamples; l0 += launch_max) {
+        const uint64_t l1 = std::min(nsamples, l0 + launch_max);
         std::vector<DevPiece> dev;
-        uint32_t smem_entries = 0;
+        std::vector<uint64_t> dev_len;
         while (first_piece < pieces.size() && pieces[first_piece].k_end <= l0) first_piece++;
         for (size_t i = first_piece; i < pieces.size() && pieces[i].k_begin < l1; i++) {
             const dplan::Piece& pc = pieces[i];
@@ -195,21 +215,29 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
             } else {
                 d.base = (uint32_t)(((uint64_t)pc.base + delta) % pc.period);
                 magic_for(pc.period, &d.magic, &d.shift);
-                d.step_u = (uint32_t)((uint64_t)(dmix::kThreads * G) % pc.period);
+                d.step_u = shape.row_samples % pc.period;
                 int rc = get_table(ctx, pc.r, pc.period, pc.k_end - pc.k_begin, s, &d.tab);
                 if (rc) return rc;
-                if (d.tab != dmix::kNoTab && pc.period <= kSmemTabMaxEntries) smem_entries = std::max(smem_entries, pc.period);
             }
             dev.push_back(d);
+            dev_len.push_back(e - b);
         }
         // get_table may have recycled the arena: offsets taken earlier in this launch would
         // dangle.  Re-resolve every tabled piece against the final cache (cheap, rare).
-        for (DevPiece& d : dev) {
+        uint32_t smem_piece = dmix::kNoPiece;
+        uint64_t smem_piece_len = 0;
+        for (size_t i = 0; i < dev.size(); i++) {
+            DevPiece& d = dev[i];
             if (d.tab == dmix::kNoTab) continue;
             uint32_t key;
             memcpy(&key, &d.r, 4);
             auto it = ctx->tables.find(key);
             d.tab = (it != ctx->tables.end() && it->second.period == d.period) ? it->second.off : dmix::kNoTab;
+            // one table per launch is staged in shared memory: the eligible piece covering most samples
+            if (d.tab != dmix::kNoTab && d.period <= kSmemTabMaxEntries && dev_len[i] > smem_piece_len) {
+                smem_piece = (uint32_t)i;
+                smem_piece_len = dev_len[i];
+            }
         }
 
         MixArgs a;
@@ -219,8 +247,8 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         a.tables = ctx->arena;
         a.nsamples = (uint32_t)(l1 - l0);
         a.npieces = (uint32_t)dev.size();
-        a.ntiles = (a.nsamples + tile - 1) / tile;
-        a.smem_entries = smem_entries;
+        a.ntiles = a.nsamples / shape.tile_samples;   // full tiles; the ragged end is mixed from global memory
+        a.smem_piece = smem_piece;
         DevPiece* d_pieces = nullptr;
         if (dev.size() <= (size_t)dmix::kInlinePieces) {
             for (size_t i = 0; i < dev.size(); i++) a.inl[i] = dev[i];
@@ -229,12 +257,11 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
             CUDA_TRY(ctx, cudaMemcpyAsync(d_pieces, dev.data(), dev.size() * sizeof(DevPiece), cudaMemcpyHostToDevice, s));
             a.pieces = d_pieces;
         }
-        const int occ = std::max(1, ctx->occ[intype][outtype]);
-        const uint32_t target = (uint32_t)(ctx->sm_count * occ * 4);
-        a.tiles_per_cta = std::max<uint32_t>(1, (a.ntiles + target - 1) / target);
-        const uint32_t grid = (a.ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
-        const size_t smem = smem_entries ? (smem_entries + dmix::kTabPad) * sizeof(float2) : 0;
-        kern<<<grid, dmix::kThreads, smem, s>>>(a);
+        // persistent: one CTA per SM, every warp an independent pipeline over interleaved tiles
+        const uint32_t want = (a.ntiles + shape.warps - 1) / shape.warps;
+        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->sm_count, want));
+        const size_t smem = shape.fixed_smem + (smem_piece != dmix::kNoPiece ? shape.table_bytes(dev[smem_piece].period) : 0);
+        shape.kern<<<grid, shape.warps * 32, smem, s>>>(a);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
         if (d_pieces) CUDA_TRY(ctx, cudaFreeAsync(d_pieces, s));
@@ -406,11 +433,9 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->tables_ready, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e2 == cudaSuccess; i++)
         for (int o = 0; o < 2 && e2 == cudaSuccess; o++) {
-            MixKernel k = mix_kernel_for(i, o);
-            e2 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((kSmemTabMaxEntries + dmix::kTabPad) * sizeof(float2)));
-            if (e2 == cudaSuccess)
-                e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[i][o], k, dmix::kThreads, 4096);
+            const StreamShape& sh = shape_for(i, o);
+            e2 = cudaFuncSetAttribute(sh.kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sh.fixed_smem + sh.table_bytes(kSmemTabMaxEntries)));
         }
     if (e2 != cudaSuccess) {
         fail(nullptr, DOPPLER_B200_ECUDA, "context setup failed: %s", cudaGetErrorString(e2));

@@ -71,6 +71,7 @@ struct MixArgs {
     uint32_t tiles_per_cta;
     uint32_t smem_entries;    // capacity of the shared-memory table (excluding pad)
     uint32_t interleave;      // 0: CTA b owns tiles [b*tiles_per_cta, (b+1)*tiles_per_cta); 1: tiles b, b+grid, ...
+    uint32_t smem_piece;      // streaming kernel: piece whose table is staged in shared memory, or kNoPiece
     DevPiece inl[kInlinePieces];
 };
 
@@ -318,6 +319,324 @@ __global__ void __launch_bounds__(T, MINB) mix_kernel(const __grid_constant__ Mi
             fast_tile<IN, OUT, kTabShared, T, U>(a, p, k0, tab_s);
         } else {
             fast_tile<IN, OUT, kTabGlobal, T, U>(a, p, k0, a.tables + p.tab);
+        }
+    }
+}
+
+// =============================================================================================
+// Streaming kernel: every warp is an independent bulk-async (TMA 1-D) pipeline.
+//
+// Measured on B200 (profiles/r01_tune_*.md): a register-staged LDG/STG loop tops out at
+// 0.85-0.93 of the measured copy peak however it is shaped, while cp.async.bulk pipelines reach
+// 0.99-1.02 when -- and only when -- about 32-48 KB of loads are in flight per SM (more in
+// flight is *slower*: 0.93-0.95).  So the mixer moves its tiles with cp.async.bulk: global ->
+// shared (mbarrier complete_tx), compute from shared into shared, shared -> global (bulk
+// group).  Bytes in flight are set by WARPS x S x tile bytes, not by registers or occupancy.
+//
+// One CTA per SM, WARPS warps, no CTA-wide barrier after start-up.  Warp w of CTA b is
+// pipeline p = b * WARPS + w and owns tiles p, p + npipes, ... (interleaved, so the whole chip
+// walks one moving window of the stream).  Per tile and warp:
+//     wait full[s]  ->  LDS the tile into registers  ->  lane 0: wait until the bulk store that
+//     last used out[s] has drained  ->  syncwarp  ->  lane 0: refill in[s] with tile i + S  ->
+//     multiply, STS into out[s]  ->  fence.proxy.async  ->  syncwarp  ->  lane 0: bulk store
+// The shared-memory phasor table is de-interleaved into G planes (entry e -> plane e mod G) so
+// that the warp's lookups (lane l needs entries j + G*l + s) are bank-conflict free.
+constexpr uint32_t kNoPiece = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t cnt)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(cnt));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int IN, int OUT, int WARPS_, int S_, int U_>
+struct StreamCfg {
+    static constexpr int WARPS = WARPS_, S = S_, U = U_;
+    static constexpr int G = group_samples(IN, OUT);
+    static constexpr int kGroupIn = G * (IN == I16 ? 4 : 8);
+    static constexpr int kGroupOut = G * (OUT == I16 ? 4 : 8);
+    static constexpr int kRow = 32 * G;                     // samples per warp-row (one group per lane)
+    static constexpr int kTileSamples = kRow * U;
+    static constexpr int kTileIn = 32 * U * kGroupIn;
+    static constexpr int kTileOut = 32 * U * kGroupOut;
+    static constexpr int kRing = S * (kTileIn + kTileOut);  // per warp
+    static constexpr int kBarBytes = ((WARPS * S * 8 + 127) / 128) * 128;
+    static constexpr int kFixedSmem = kBarBytes + WARPS * kRing;
+    // shared-memory table: G planes of plane_len(entries) float2 each
+    __host__ __device__ static constexpr uint32_t plane_len(uint32_t period) { return (period + kRow + G - 1) / G + 1; }
+    __host__ __device__ static constexpr uint32_t table_bytes(uint32_t period) { return G * plane_len(period) * 8; }
+};
+
+// i16 -> i16 only: the 2^-15 ingest scale (dsp.rs:91) is deferred into the egress constant.
+// a = i * 2^-15 is exact, so fl(a*c) = fl(i*c) * 2^-15 and fl(re * 32767) = fl(re' * (32767 * 2^-15))
+// bit for bit (power-of-two scaling commutes with rounding; the only exceptions are values
+// below 2^-100, which truncate to 0 on the i16 egress either way).  Saves 2 FMUL per sample.
+template <int IN, int OUT>
+struct Scaling {
+    static constexpr bool kDeferred = (IN == I16 && OUT == I16);
+};
+
+template <int IN, int OUT, int G>
+__device__ __forceinline__ void unpack_group(const uint32_t (&w)[4], float2 (&s)[G])
+{
+    if constexpr (IN == I16) {
+#pragma unroll
+        for (int i = 0; i < G; i++) {
+            if constexpr (Scaling<IN, OUT>::kDeferred) {
+                s[i] = make_float2(__int2float_rn((int)(short)(w[i] & 0xffffu)), __int2float_rn((int)(short)(w[i] >> 16)));
+            } else {
+                s[i] = ingest_i16(w[i]);
+            }
+        }
+    } else {
+        s[0] = make_float2(__uint_as_float(w[0]), __uint_as_float(w[1]));
+        s[1] = make_float2(__uint_as_float(w[2]), __uint_as_float(w[3]));
+    }
+}
+
+template <int IN, int OUT>
+__device__ __forceinline__ uint32_t egress_i16_scaled(float2 v)
+{
+    if constexpr (Scaling<IN, OUT>::kDeferred) {
+        short i, q;
+        const float fi = __fmul_rn(v.x, 0x1.fffcp-1f /* 32767 * 2^-15 */);
+        const float fq = __fmul_rn(v.y, 0x1.fffcp-1f);
+        asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(i) : "f"(fi));
+        asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(q) : "f"(fq));
+        return (uint32_t)(uint16_t)i | ((uint32_t)(uint16_t)q << 16);
+    } else {
+        return egress_i16(v);
+    }
+}
+
+// e in [0, period + kRow) -> e mod period (periods shorter than a row need the real modulo)
+__device__ __forceinline__ uint32_t wrap_phase(uint32_t e, uint32_t period)
+{
+    if (e >= period) {
+        e -= period;
+        if (e >= period) e %= period;
+    }
+    return e;
+}
+
+// One full tile inside one piece, from the warp's shared-memory stage.
+template <typename C, int IN, int OUT, int MODE>
+__device__ __forceinline__ void stream_tile(const uint32_t (&raw)[C::U][4], unsigned char* out_s, const DevPiece& p, uint32_t k0,
+                                            const float2* tab, uint32_t plane_len, uint32_t lane)
+{
+    constexpr int G = C::G, U = C::U;
+    // phase index of the row's first sample (warp-uniform); lanes add G * lane
+    const uint32_t off0 = k0 - p.k_begin;
+    uint32_t j = 0;
+    if constexpr (MODE != kDirectLinear) j = piece_samplenum(p, off0) - 1u;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        float2 smp[G], res[G];
+        unpack_group<IN, OUT, G>(raw[u], smp);
+#pragma unroll
+        for (int s = 0; s < G; s++) {
+            float2 ph;
+            if constexpr (MODE == kTabShared) {
+                const uint32_t e = j + (uint32_t)s;                          // uniform part of the entry index
+                ph = tab[(e % G) * plane_len + e / G + lane];                // entry e + G*lane, plane (e mod G)
+            } else if constexpr (MODE == kTabGlobal) {
+                ph = __ldg(tab + wrap_phase(j + lane * G + (uint32_t)s, p.period));
+            } else if constexpr (MODE == kDirectPeriodic) {
+                ph = phasor(p.r, wrap_phase(j + lane * G + (uint32_t)s, p.period) + 1u);
+            } else {
+                ph = phasor(p.r, p.base + off0 + (uint32_t)(u * C::kRow + s) + lane * G);
+            }
+            res[s] = cmul_unfused(smp[s], ph);
+        }
+        unsigned char* dst = out_s + (u * 32 + lane) * C::kGroupOut;
+        if constexpr (OUT == I16 && G == 4) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(egress_i16_scaled<IN, OUT>(res[0]), egress_i16_scaled<IN, OUT>(res[1]),
+                                                        egress_i16_scaled<IN, OUT>(res[2]), egress_i16_scaled<IN, OUT>(res[3]));
+        } else if constexpr (OUT == I16) {
+            *reinterpret_cast<uint2*>(dst) = make_uint2(egress_i16(res[0]), egress_i16(res[1]));
+        } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(res[0].x, res[0].y, res[1].x, res[1].y);
+        }
+        if constexpr (MODE != kDirectLinear) {
+            j += p.step_u;
+            if (j >= p.period) j -= p.period;
+        }
+    }
+}
+
+// A full tile that straddles pieces: per-sample piece lookup and direct phasor, still staged.
+template <typename C, int IN, int OUT>
+__device__ __noinline__ void stream_tile_slow(const MixArgs& a, uint32_t pi, const unsigned char* in_s, unsigned char* out_s,
+                                              uint32_t k0, uint32_t lane)
+{
+    DevPiece p = get_piece(a, pi);
+    for (uint32_t i = lane; i < (uint32_t)C::kTileSamples; i += 32) {
+        const uint32_t k = k0 + i;
+        if (k >= p.k_end) {
+            pi = find_piece(a, pi, k);
+            p = get_piece(a, pi);
+        }
+        const float2 ph = phasor(p.r, piece_samplenum(p, k - p.k_begin));
+        float2 smp;
+        if constexpr (IN == I16)
+            smp = ingest_i16(reinterpret_cast<const uint32_t*>(in_s)[i]);
+        else
+            smp = reinterpret_cast<const float2*>(in_s)[i];
+        const float2 v = cmul_unfused(smp, ph);
+        if constexpr (OUT == I16)
+            reinterpret_cast<uint32_t*>(out_s)[i] = egress_i16(v);
+        else
+            reinterpret_cast<float2*>(out_s)[i] = v;
+    }
+}
+
+template <int IN, int OUT, int WARPS, int S, int U>
+__global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_constant__ MixArgs a)
+{
+    using C = StreamCfg<IN, OUT, WARPS, S, U>;
+    constexpr int G = C::G;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    unsigned char* rings = smem + C::kBarBytes;
+    float2* tab_s = reinterpret_cast<float2*>(smem + C::kFixedSmem);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* full = bars + warp * S;
+    unsigned char* ring_in = rings + warp * C::kRing;
+    unsigned char* ring_out = ring_in + S * C::kTileIn;
+
+    // start-up: barriers + (optionally) one piece's table de-interleaved into shared memory
+    uint32_t plane_len = 0;
+    if (a.smem_piece != kNoPiece) {
+        const DevPiece sp = get_piece(a, a.smem_piece);
+        plane_len = C::plane_len(sp.period);
+        const float2* src = a.tables + sp.tab;
+        for (uint32_t e = threadIdx.x; e < sp.period + (uint32_t)C::kRow; e += WARPS * 32)
+            tab_s[(e % G) * plane_len + e / G] = __ldg(src + e % sp.period);   // replicated past the period: no wrap in a row
+    }
+    if (lane == 0) {
+        for (int s = 0; s < S; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t pipe = blockIdx.x * WARPS + warp, npipes = gridDim.x * WARPS;
+    const uint32_t ntiles = a.ntiles;   // full tiles
+    const uint32_t mine = pipe < ntiles ? (ntiles - pipe + npipes - 1) / npipes : 0;
+    const unsigned char* gin = static_cast<const unsigned char*>(a.in);
+    unsigned char* gout = static_cast<unsigned char*>(a.out);
+
+    auto issue_load = [&](uint32_t i) {   // lane 0 only
+        const uint32_t s = i % S;
+        mbar_expect_tx(&full[s], C::kTileIn);
+        bulk_g2s(ring_in + s * C::kTileIn, gin + (size_t)(pipe + i * npipes) * C::kTileIn, C::kTileIn, &full[s]);
+    };
+    if (lane == 0)
+        for (uint32_t i = 0; i < (uint32_t)S && i < mine; i++) issue_load(i);
+
+    uint32_t pi = 0;
+    DevPiece p = get_piece(a, 0);
+    for (uint32_t i = 0; i < mine; i++) {
+        const uint32_t s = i % S;
+        const uint32_t tile = pipe + i * npipes;
+        const uint32_t k0 = tile * C::kTileSamples;
+        const unsigned char* in_s = ring_in + s * C::kTileIn;
+        unsigned char* out_s = ring_out + s * C::kTileOut;
+        if (k0 >= p.k_end) {
+            pi = find_piece(a, pi, k0);
+            p = get_piece(a, pi);
+        }
+        const bool fast = k0 + C::kTileSamples <= p.k_end;
+        mbar_wait(&full[s], (i / S) & 1u);
+        if (fast) {
+            uint32_t raw[U][4];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const unsigned char* src = in_s + (u * 32 + lane) * C::kGroupIn;
+                if constexpr (C::kGroupIn == 16) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(src);
+                    raw[u][0] = w.x, raw[u][1] = w.y, raw[u][2] = w.z, raw[u][3] = w.w;
+                } else {
+                    const uint2 w = *reinterpret_cast<const uint2*>(src);
+                    raw[u][0] = w.x, raw[u][1] = w.y, raw[u][2] = 0, raw[u][3] = 0;
+                }
+            }
+            if (lane == 0) bulk_wait_read<S - 1>();   // the store that last read out[s] (tile i - S) has drained
+            __syncwarp();
+            if (lane == 0 && i + S < mine) issue_load(i + S);   // in[s] is in registers now: refill it
+            if (p.period == 0)
+                stream_tile<C, IN, OUT, kDirectLinear>(raw, out_s, p, k0, nullptr, 0, lane);
+            else if (p.tab == kNoTab)
+                stream_tile<C, IN, OUT, kDirectPeriodic>(raw, out_s, p, k0, nullptr, 0, lane);
+            else if (pi == a.smem_piece)
+                stream_tile<C, IN, OUT, kTabShared>(raw, out_s, p, k0, tab_s, plane_len, lane);
+            else
+                stream_tile<C, IN, OUT, kTabGlobal>(raw, out_s, p, k0, a.tables + p.tab, 0, lane);
+        } else {
+            if (lane == 0) bulk_wait_read<S - 1>();
+            __syncwarp();
+            stream_tile_slow<C, IN, OUT>(a, pi, in_s, out_s, k0, lane);
+            __syncwarp();
+            if (lane == 0 && i + S < mine) issue_load(i + S);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(gout + (size_t)tile * C::kTileOut, out_s, C::kTileOut);
+            bulk_commit();
+        }
+    }
+    if (lane == 0) bulk_wait_all();
+
+    // ragged end of the buffer (fewer samples than a tile; may not be 16-byte granular): the
+    // pipeline next in line mixes it straight from global memory, sample by sample
+    const uint32_t tail0 = ntiles * C::kTileSamples;
+    if (tail0 < a.nsamples && pipe == ntiles % npipes) {
+        pi = find_piece(a, 0, tail0);
+        p = get_piece(a, pi);
+        for (uint32_t k = tail0 + lane; k < a.nsamples; k += 32) {
+            if (k >= p.k_end) {
+                pi = find_piece(a, pi, k);
+                p = get_piece(a, pi);
+            }
+            const float2 ph = phasor(p.r, piece_samplenum(p, k - p.k_begin));
+            store_sample<OUT>(a.out, k, cmul_unfused(load_sample<IN>(a.in, k), ph));
         }
     }
 }

@@ -169,6 +169,23 @@ def plan_trace(samplenum, shifts_hz, block_samples, samplerate, count):
     return trace, sn.value, int(npieces)
 
 
+def doppler_hz(range_rate_km_sec, frequency):
+    """main.rs:163."""
+    return float(_lib.load().doppler_b200_doppler_hz(float(range_rate_km_sec), int(frequency)))
+
+
+def replay_schedule(doppler_hz_by_second, offset, samplerate, intype, in_len):
+    """The f32 shift of every 8192-byte block as the reference's replay driver forms it (main.rs:155-184)."""
+    tab = np.ascontiguousarray(doppler_hz_by_second, dtype=np.float64)
+    cap = in_len // BUFFER_SIZE + 1
+    out = np.empty(cap, dtype=np.float32)
+    n = _lib.load().doppler_b200_replay_schedule(_ptr(tab), tab.size, int(offset), int(samplerate), int(intype), int(in_len),
+                                                 _ptr(out), cap)
+    if n == 0:
+        raise DopplerError(EINVAL, "bad replay_schedule arguments")
+    return out[:n]
+
+
 # ---- module-level functions with the reference's names (default context on cuda:0) ---------
 _default = None
 

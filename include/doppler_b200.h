@@ -130,6 +130,55 @@ uint32_t doppler_b200_samplenum_advance(uint32_t samplenum, float shift_hz, uint
 uint32_t doppler_b200_samplenum_advance_blocks(uint32_t samplenum, const float* shift_hz_per_block, size_t nblocks,
                                                uint64_t block_samples, uint32_t samplerate, uint64_t count);
 
+/* ---- track mode's Doppler schedule (host only, no GPU needed) ------------------------------ */
+
+/* src/main.rs:163: doppler_hz = (range_rate_km_sec * 1000 / c) * frequency * (-1), in f64. */
+double doppler_b200_doppler_hz(double range_rate_km_sec, uint32_t frequency);
+
+/* src/main.rs:177: the f32 shift handed to the mixer, `doppler_hz as f32 + offset as f32`. */
+float doppler_b200_track_shift(double doppler_hz, int32_t offset);
+
+/* src/main.rs:166: whole seconds of stream time after sample_count samples,
+ * `(sample_count as f32 / samplerate as f32) as i64` (f32 arithmetic, saturating cast). */
+int64_t doppler_b200_replay_seconds(uint64_t sample_count, uint32_t samplerate);
+
+/* The replay driver's clock, src/main.rs:155-184, with the propagator abstracted as a table:
+ * doppler_hz_by_second[s] = the value main.rs:163 yields at start_time + s seconds (index clamped
+ * to nsec-1).  Writes the f32 shift the reference uses for every BUFFER_SIZE-byte block of an
+ * in_len-byte recording -- block b is evaluated at the whole second reached by the samples
+ * counted before block b-1 (one-block lag) -- and returns the number of blocks the reference
+ * pumps, in_len / BUFFER_SIZE + 1 (the last one short or empty).  At most `cap` values are
+ * written.  Feed the result to doppler_b200_mix_blocks with block_bytes = BUFFER_SIZE. */
+size_t doppler_b200_replay_schedule(const double* doppler_hz_by_second, size_t nsec, int32_t offset, uint32_t samplerate,
+                                    int intype, size_t in_len, float* shifts_out, size_t cap);
+
+/* ---- orbit propagation for track mode (host only; replaces crate gpredict / libgpredict) --- */
+
+/* Tle::from_file + Predict::new (src/main.rs:141-149): TLE `tlename` from `tlefile`, observer at
+ * lat/lon (degrees) and altitude (metres).  SGP4 near-earth model (Spacetrack Report No. 3);
+ * deep-space element sets and bad checksums are rejected (EINVAL, see
+ * doppler_b200_tracker_last_error).  Parity with libgpredict is UNPINNED (not available offline);
+ * the propagator is verified against the report's own test case instead. */
+typedef struct doppler_b200_tracker doppler_b200_tracker;
+int doppler_b200_tracker_create(const char* tlefile, const char* tlename, double lat_deg, double lon_deg, double alt_m,
+                                doppler_b200_tracker** out);
+int doppler_b200_tracker_create_from_lines(const char* name, const char* line1, const char* line2, double lat_deg, double lon_deg,
+                                           double alt_m, doppler_b200_tracker** out);
+void doppler_b200_tracker_destroy(doppler_b200_tracker* tr);
+const char* doppler_b200_tracker_last_error(void);
+
+/* Predict::update(Some(t)) (src/main.rs:162) and the fields the reference reads afterwards
+ * (main.rs:163,170-173).  unix_seconds is UTC. */
+int doppler_b200_tracker_observe(doppler_b200_tracker* tr, double unix_seconds, double* az_deg, double* el_deg, double* range_km,
+                                 double* range_rate_km_sec);
+
+/* Bare SGP4 state (TEME, km and km/s) at `minutes_since_epoch`: verification hook. */
+int doppler_b200_tracker_teme(doppler_b200_tracker* tr, double minutes_since_epoch, double* pos_km, double* vel_km_s);
+
+/* doppler_hz (main.rs:163) at start, start+1 s, ... : the table doppler_b200_replay_schedule takes. */
+size_t doppler_b200_tracker_doppler_table(doppler_b200_tracker* tr, double start_unix_seconds, uint32_t frequency, size_t nsec,
+                                          double* doppler_hz_out);
+
 /* Test/introspection hook: expands the planner's closed-form pieces into the per-sample
  * samplenum sequence (trace[k] = value used for sample k) for a per-block schedule.  Returns
  * the number of pieces, *samplenum advanced. */

@@ -38,6 +38,7 @@ def _native_built():
         os.path.join(ROOT, "oracle", "liboracle.so"),
         os.path.join(ROOT, "tests", "native", "libhostcheck.so"),
         os.path.join(ROOT, "doppler_b200", "libdoppler_b200.so"),
+        os.path.join(ROOT, "doppler_b200", "bin", "doppler"),
     ]
     if not all(os.path.exists(p) for p in need):
         import __graft_entry__

@@ -1,0 +1,170 @@
+"""The `doppler` CLI (doppler_b200/csrc/doppler_cli.cpp): argv contract of the reference's
+src/usage.rs on the CPU, and byte-exact stdout against the oracle's stream drivers (restating
+src/main.rs:102-119 and :155-184) on the GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.oracle_lib import BUFFER_SIZE, F32, I16
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "doppler_b200", "bin", "doppler")
+
+L1 = "1 88888U          80275.98708465  .00073094  13844-3  66816-4 0    87"
+L2 = "2 88888  72.8435 115.9689 0086731  52.6988 110.5714 16.05824518  1058"
+
+
+def run(args, stdin=b"", timeout=120):
+    return subprocess.run([CLI] + args, input=stdin, capture_output=True, timeout=timeout)
+
+
+def tone_i16(n, fs, seed):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    sig = 0.25 * np.exp(2j * np.pi * 15000.0 / fs * t) + 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    iq = np.empty(2 * n, dtype="<i2")
+    iq[0::2] = np.clip(np.round(sig.real * 32767), -32768, 32767)
+    iq[1::2] = np.clip(np.round(sig.imag * 32767), -32768, 32767)
+    return iq.view(np.uint8)
+
+
+# ---- argv contract (no GPU needed: every one of these exits before the device is opened) -------
+
+def test_no_subcommand_exits_1():
+    r = run([])
+    assert r.returncode == 1 and b"no arguments provided, try with doppler -h" in r.stderr   # usage.rs:330-333
+
+
+def test_help_and_version():
+    assert run(["--help"]).returncode == 0
+    assert b"--shift" in run(["const", "--help"]).stdout
+    assert b"--tlename" in run(["track", "-h"]).stdout
+    assert run(["--version"]).stdout.startswith(b"doppler ")
+
+
+@pytest.mark.parametrize("args", [
+    ["const", "-s", "256000", "-i", "i16"],                       # --shift required (usage.rs:153-157)
+    ["const", "-i", "i16", "--shift", "5"],                       # --samplerate required
+    ["const", "-s", "256000", "--shift", "5"],                    # --intype required
+    ["const", "-s", "256000", "-i", "u8", "--shift", "5"],        # possible_values
+    ["const", "-s", "abc", "-i", "i16", "--shift", "5"],          # value_t_or_exit!
+    ["const", "-s", "256000", "-i", "i16", "--shift", "5.5"],     # i32
+    ["const", "-s", "256000", "-i", "i16", "--shift", "3000000000"],
+    ["const", "-s", "256000", "-i", "i16", "--shift", "5", "--bogus", "1"],
+    ["track", "-s", "256000", "-i", "i16", "--tlename", "X", "--location", "lat=1,lon=2,alt=3", "--frequency", "1"],   # --tlefile
+    ["track", "-s", "256000", "-i", "i16", "--tlefile", "f", "--tlename", "X", "--location", "lat=1,lon=2", "--frequency", "1"],
+    ["track", "-s", "256000", "-i", "i16", "--tlefile", "f", "--tlename", "X", "--location", "lat=a,lon=2,alt=3", "--frequency", "1"],
+    ["track", "-s", "256000", "-i", "i16", "--tlefile", "f", "--tlename", "X", "--location", "lat=1,lon=2,alt=3", "--frequency", "1",
+     "--time", "2015-01-22 09:07:16"],                             # usage.rs:302-311
+    ["track", "-s", "256000", "-i", "i16", "--tlefile", "/nonexistent", "--tlename", "X", "--location", "lat=1,lon=2,alt=3",
+     "--frequency", "1", "--time", "2015-01-22T09:07:16"],         # main.rs:141-147
+])
+def test_bad_arguments_exit_1(args):
+    r = run(args)
+    assert r.returncode == 1, r.stderr
+    assert r.stdout == b""
+
+
+def test_tle_errors_exit_1(tmp_path):
+    f = tmp_path / "t.txt"
+    f.write_text("SAT\n" + L1[:-1] + "0\n" + L2 + "\n")
+    base = ["track", "-s", "256000", "-i", "i16", "--tlefile", str(f), "--location", "lat=1,lon=2,alt=3", "--frequency", "1",
+            "--time", "2015-01-22T09:07:16"]
+    r = run(base + ["--tlename", "SAT"])
+    assert r.returncode == 1 and b"checksum" in r.stderr
+    r = run(base + ["--tlename", "NOPE"])
+    assert r.returncode == 1 and b"not found" in r.stderr
+
+
+# ---- stream parity (GPU) ------------------------------------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [256000, 255999, 2048 * 3, 0, 5])
+def test_const_cfg1_matches_reference_stream(oracle, n):
+    """BASELINE configs[0]: 1 s of i16 IQ @ 256 ksps, --shift -15000 (and the short-last-block variants)."""
+    x = tone_i16(n, 256000, 20150122)
+    want, _, panicked = oracle.const_stream(x, I16, I16, -15000, 256000)
+    assert not panicked
+    r = run(["const", "-s", "256000", "-i", "i16", "--shift", "-15000"], x.tobytes())
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == want.tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("intype,outtype,flags", [(F32, I16, ["-i", "f32", "-o", "i16"]), (I16, F32, ["--intype=i16", "--outtype=f32"]),
+                                                  (F32, F32, ["-if32"])])
+def test_const_type_pairs_and_flag_spellings(oracle, intype, outtype, flags):
+    rng = np.random.default_rng(3)
+    n = 70_001
+    x = (rng.uniform(-0.7, 0.7, 2 * n).astype("<f4") if intype == F32 else rng.integers(-32768, 32768, 2 * n).astype("<i2")).view(np.uint8)
+    want, _, panicked = oracle.const_stream(x, intype, outtype, 100000, 10_000_000)
+    assert not panicked
+    r = run(["const", "--samplerate", "10000000", "--shift", "100000"] + flags, x.tobytes())
+    assert r.returncode == 0, r.stderr
+    got = np.frombuffer(r.stdout, dtype=np.uint8)
+    if outtype == I16:
+        assert np.array_equal(got, want)
+    else:
+        from tests.oracle_lib import same_bits_f32
+        assert same_bits_f32(got, want)
+
+
+@pytest.mark.gpu
+def test_misaligned_tail_panics_after_writing_the_full_blocks(oracle):
+    """dsp.rs:87: the converter's assert fires on the short last block; earlier blocks are already out."""
+    x = tone_i16(2048 * 2 + 10, 256000, 1).tobytes() + b"\x01\x02"
+    want, _, panicked = oracle.const_stream(np.frombuffer(x, dtype=np.uint8), I16, I16, -15000, 256000)
+    assert panicked
+    r = run(["const", "-s", "256000", "-i", "i16", "--shift", "-15000"], x)
+    assert r.returncode == 101 and b"panicked" in r.stderr
+    assert r.stdout == want.tobytes()
+
+
+@pytest.mark.gpu
+def test_track_replay_from_doppler_table_matches_reference_stream(oracle, tmp_path):
+    fs, secs = 1_024_000, 4
+    t = np.arange(secs + 2, dtype=np.float64)
+    rr = 7.5 * 7.5 * (t - 2.0) / np.sqrt(700.0 ** 2 + (7.5 * (t - 2.0)) ** 2)
+    table = np.array([oracle.doppler_hz(v, 437_505_000) for v in rr])
+    f = tmp_path / "doppler.txt"
+    f.write_text("\n".join(repr(float(v)) for v in table))
+    x = tone_i16(secs * fs - 123, fs, 1024000)
+    want, _, _, panicked = oracle.track_replay_stream(x, I16, I16, table, 5000, fs)
+    assert not panicked
+    r = run(["track", "-s", str(fs), "-i", "i16", "--doppler-table", str(f), "--offset", "5000", "--time", "2015-01-22T09:07:16"], x.tobytes())
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == want.tobytes()
+
+
+@pytest.mark.gpu
+def test_track_replay_with_tle_matches_library_schedule(oracle, tmp_path):
+    """README's replay command line (synthetic element set: Spacetrack Report 3's test satellite, NOT
+    a real ESTCube-1 TLE).  CLI stdout == mix_blocks fed by the tracker's per-second Doppler table."""
+    import ctypes
+    from doppler_b200 import _lib, dsp
+    import doppler_b200
+    f = tmp_path / "cubesat.txt"
+    f.write_text("SYNTHETIC TEST SAT\n" + L1 + "\n" + L2 + "\n")
+    fs, secs = 256000, 7
+    x = tone_i16(secs * fs + 77, fs, 9)
+    lib = _lib.load()
+    tr = ctypes.c_void_p()
+    assert lib.doppler_b200_tracker_create(str(f).encode(), b"SYNTHETIC TEST SAT", 58.26541, 26.46667, 76.0, ctypes.byref(tr)) == 0
+    start = (np.datetime64("1980-10-02T00:10:00") - np.datetime64("1970-01-01T00:00:00")) / np.timedelta64(1, "s")
+    table = np.zeros(secs + 2)
+    lib.doppler_b200_tracker_doppler_table(tr, float(start), 437_505_000, table.size, table.ctypes.data)
+    lib.doppler_b200_tracker_destroy(tr)
+    assert np.ptp(table) > 1.0   # the Doppler actually moves over the recording
+    shifts = dsp.replay_schedule(table, -2500, fs, I16, x.size)
+    m = doppler_b200.Mixer(0)
+    want, _ = m.mix_blocks(x, I16, I16, shifts, fs)
+    m.close()
+    want_o, _, _, _ = oracle.track_replay_stream(x, I16, I16, table, -2500, fs)
+    assert np.array_equal(want, want_o)
+    r = run(["track", "-s", str(fs), "-i", "i16", "--tlefile", str(f), "--tlename", "SYNTHETIC TEST SAT", "--location",
+             "lat=58.26541,lon=26.46667,alt=76", "--frequency", "437505000", "--offset", "-2500", "--time", "1980-10-02T00:10:00"], x.tobytes())
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == want.tobytes()
+    assert b"range rate" in r.stderr   # main.rs:167-175 telemetry every 5 s of stream time

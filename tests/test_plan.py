@@ -93,3 +93,22 @@ def test_slices_compose(oracle):
         seed = dsp.samplenum_advance(0, shift, fs, a)
         part, _, _ = dsp.plan_trace(seed, [shift], b - a, fs, b - a)
         assert np.array_equal(part, whole[a:b])
+
+
+# ---- track mode's Doppler schedule (replay.cpp) against the oracle's replay driver -------------
+
+@pytest.mark.parametrize("intype", [0, 1])
+@pytest.mark.parametrize("fs", [8192, 256000, 1_024_000, 3])
+def test_replay_schedule_matches_reference_clock(oracle, intype, fs):
+    """main.rs:155-184: per-block f32 shift with the one-block lag and f32 second arithmetic."""
+    t = np.arange(40, dtype=np.float64)
+    rr = 7.5 * 7.5 * (t - 17.0) / np.sqrt(700.0 ** 2 + (7.5 * (t - 17.0)) ** 2)
+    table = np.array([oracle.doppler_hz(x, 437_505_000) for x in rr])
+    assert [dsp.doppler_hz(x, 437_505_000) for x in rr] == list(table)
+    bps = 4 if intype == 0 else 8
+    for nbytes in (0, bps, 8192, 8192 * 7 + bps * 3, 8192 * 40, 8192 * 133 + bps):
+        x = np.zeros(nbytes, dtype=np.uint8)
+        _, _, used, panicked = oracle.track_replay_stream(x, intype, intype, table, -2500, fs)
+        assert not panicked
+        got = dsp.replay_schedule(table, -2500, fs, intype, nbytes)
+        assert np.array_equal(used.view(np.uint32), got.view(np.uint32)), (nbytes, fs)

@@ -310,6 +310,73 @@ static void run_bulk(uint64_t bytes, uint32_t tile_bytes, int ctas_per_sm, int n
     report(name, (uint64_t)ntiles * tile_bytes / 4, 8, tm, extra);
 }
 
+template <int IN, int OUT, int WARPS, int S, int U>
+static void run_stream(uint64_t n, uint32_t period, float r, int tabmode /*0 smem, 1 global(L2), 2 direct*/)
+{
+    using C = dmix::StreamCfg<IN, OUT, WARPS, S, U>;
+    char name[160];
+    snprintf(name, sizeof name, "stream %s->%s W%d S%d U%d %s P%u", tname(IN), tname(OUT), WARPS, S, U,
+             tabmode == 0 ? "smemtab" : tabmode == 1 ? "l2tab" : "direct", period);
+    if (!want(name)) return;
+    auto kern = dmix::mix_stream_kernel<IN, OUT, WARPS, S, U>;
+    const size_t smem = C::kFixedSmem + (tabmode == 0 ? C::table_bytes(period) : 0);
+    if (smem > 227 * 1024) return;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, kern));
+    MixArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = g_buf.in;
+    a.out = g_buf.out;
+    a.tables = g_buf.tab;
+    a.nsamples = (uint32_t)n;
+    a.npieces = 1;
+    a.ntiles = (uint32_t)(n / C::kTileSamples);
+    a.smem_piece = tabmode == 0 ? 0 : dmix::kNoPiece;
+    DevPiece d;
+    memset(&d, 0, sizeof d);
+    d.k_begin = 0;
+    d.k_end = (uint32_t)n;
+    d.base = 0;
+    d.period = period;
+    d.r = r;
+    d.tab = tabmode == 2 ? dmix::kNoTab : 0;
+    magic_for(period, &d.magic, &d.shift);
+    d.step_u = (uint32_t)C::kRow % period;
+    a.inl[0] = d;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)g_sms, (a.ntiles + WARPS - 1) / WARPS);
+    Timing tm = time_it([&] { kern<<<grid, WARPS * 32, smem, g_stream>>>(a); });
+    char extra[160];
+    snprintf(extra, sizeof extra, ", \"regs\": %d, \"smem\": %d, \"inflight_kb_per_sm\": %d", fa.numRegs, (int)smem, WARPS * S * C::kTileIn / 1024);
+    report(name, n, (IN ? 8 : 4) + (OUT ? 8 : 4), tm, extra);
+}
+
+template <int IN, int OUT, int WARPS>
+static void sweep_stream_w(uint64_t n)
+{
+    const uint32_t P = 256;
+    const float r = -15000.0f / 256000.0f;
+    run_stream<IN, OUT, WARPS, 2, 1>(n, P, r, 0);
+    run_stream<IN, OUT, WARPS, 3, 1>(n, P, r, 0);
+    run_stream<IN, OUT, WARPS, 4, 1>(n, P, r, 0);
+    run_stream<IN, OUT, WARPS, 2, 2>(n, P, r, 0);
+    run_stream<IN, OUT, WARPS, 3, 2>(n, P, r, 0);
+    run_stream<IN, OUT, WARPS, 4, 2>(n, P, r, 0);
+    run_stream<IN, OUT, WARPS, 2, 3>(n, P, r, 0);
+    run_stream<IN, OUT, WARPS, 3, 3>(n, P, r, 0);
+}
+
+template <int IN, int OUT>
+static void sweep_stream(uint64_t n)
+{
+    sweep_stream_w<IN, OUT, 12>(n);
+    sweep_stream_w<IN, OUT, 16>(n);
+    sweep_stream_w<IN, OUT, 20>(n);
+    sweep_stream_w<IN, OUT, 24>(n);
+    sweep_stream_w<IN, OUT, 28>(n);
+    sweep_stream_w<IN, OUT, 32>(n);
+}
+
 template <int IN, int OUT>
 static void sweep_pair(uint64_t n)
 {
@@ -348,8 +415,8 @@ int main(int argc, char** argv)
     CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     fprintf(stderr, "device %s, %d SMs, peak %.1f GB/s\n", prop.name, g_sms, g_peak);
 
-    const uint64_t n_small = 256ull << 20;                  // 268 M samples
-    const uint64_t n_big = big ? (1000ull << 20) : n_small;   // ~1.05 G samples (< 2^30)
+    const uint64_t n_small = getenv("TUNE_N") ? strtoull(getenv("TUNE_N"), nullptr, 10) : (256ull << 20);   // 268 M samples
+    const uint64_t n_big = big ? (1000ull << 20) : std::max<uint64_t>(n_small, 256ull << 20);   // ~1.05 G samples (< 2^30)
     const uint64_t cap = n_big * 8;
     CK(cudaMalloc(&g_buf.in, cap));
     CK(cudaMalloc(&g_buf.out, cap));
@@ -363,6 +430,8 @@ int main(int argc, char** argv)
         if (f32 == 0) {
             sweep_pair<0, 0>(n_small);
             sweep_pair<0, 1>(n_small);
+            sweep_stream<0, 0>(n_small);
+            sweep_stream<0, 1>(n_small);
             if (big) {
                 run_mix<0, 0, 256, 4, 0>(n_big, 0, 0, 256, -15000.0f / 256000.0f);
                 run_mix<0, 0, 256, 4, 0>(n_big, 1, 0, 256, -15000.0f / 256000.0f);
@@ -371,6 +440,8 @@ int main(int argc, char** argv)
         } else {
             sweep_pair<1, 0>(n_small);
             sweep_pair<1, 1>(n_small);
+            sweep_stream<1, 0>(n_small);
+            sweep_stream<1, 1>(n_small);
             if (big) {
                 run_mix<1, 0, 256, 4, 0>(n_big, 0, 0, 256, -15000.0f / 256000.0f);
                 run_mix<1, 0, 256, 4, 0>(n_big, 1, 0, 256, -15000.0f / 256000.0f);
