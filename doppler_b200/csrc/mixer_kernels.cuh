@@ -98,11 +98,19 @@ __device__ __forceinline__ float2 cmul_unfused(float2 smp, float2 ph)
 }
 
 // dsp.rs:91-92: (i16 as f32) / 32768.   (exact: power-of-two scale)
+// i16 -> f32 of the low / high half of an IQ word without the slow-pipe I2F.S16 (measured ~4.5
+// issue cycles per warp against ~1.7 for LOP3 / FADD / I2FP, profiles/r01_pipes.jsonl):
+// low half by exponent bias, (2^23 + 2^15 + i) - (2^23 + 2^15), exact for every i16; high half by
+// arithmetic shift + I2FP.F32.S32.
+__device__ __forceinline__ float i16_lo_f32(uint32_t w)
+{
+    return __fsub_rn(__uint_as_float((w & 0xffffu) ^ 0x4b008000u), 8421376.0f);
+}
+__device__ __forceinline__ float i16_hi_f32(uint32_t w) { return __int2float_rn((int)w >> 16); }
+
 __device__ __forceinline__ float2 ingest_i16(uint32_t w)
 {
-    const float i = __int2float_rn((int)(short)(w & 0xffffu));
-    const float q = __int2float_rn((int)(short)(w >> 16));
-    return make_float2(__fmul_rn(i, 0x1p-15f), __fmul_rn(q, 0x1p-15f));
+    return make_float2(__fmul_rn(i16_lo_f32(w), 0x1p-15f), __fmul_rn(i16_hi_f32(w), 0x1p-15f));
 }
 
 // main.rs:77-78: (v * 32767.0) as i16 -- truncate toward zero, saturate, NaN -> 0: exactly
@@ -419,7 +427,7 @@ __device__ __forceinline__ void unpack_group(const uint32_t (&w)[4], float2 (&s)
 #pragma unroll
         for (int i = 0; i < G; i++) {
             if constexpr (Scaling<IN, OUT>::kDeferred) {
-                s[i] = make_float2(__int2float_rn((int)(short)(w[i] & 0xffffu)), __int2float_rn((int)(short)(w[i] >> 16)));
+                s[i] = make_float2(i16_lo_f32(w[i]), i16_hi_f32(w[i]));
             } else {
                 s[i] = ingest_i16(w[i]);
             }
@@ -455,16 +463,87 @@ __device__ __forceinline__ uint32_t wrap_phase(uint32_t e, uint32_t period)
     return e;
 }
 
-// One full tile inside one piece, from the warp's shared-memory stage.
+// ---------------------------------------------------------------------------------------------
+// Direct (table-free) evaluation, fast rows.
+//
+// The generic db_sincosf_glibc() costs ~115 issued instructions per sample inside the tile loop
+// (three range branches, per-lane 4/pi window lookup, literal double constants re-materialised
+// with two MOVs per use).  Inside one piece theta(n) = C * (r * f32(n)) is monotone in n (every
+// step is a correctly-rounded multiply by a constant), so the first and last sample of a tile
+// bound every sample between them: if both fall in the same glibc range -- and, in the large
+// range, the same binade -- the whole tile does, warp-uniformly, and runs a branch-free
+// evaluation of exactly that range's operation sequence:
+//   LARGE  |theta| >= 120        : glibc reduce_large.  The 96-bit window of 4/pi depends only on
+//          the exponent, so it is shifted once per tile (W = window << (e & 7), mod 2^96) and
+//          m * W replaces (m << shift) * window -- the same integer mod 2^96, hence the same res0.
+//   MEDIUM 0.75 <= |theta| < 120 : reduce_fast (one fused x - n*pi/2).
+//   SMALL  2^-12 <= |theta| < .75: polynomial pair on theta itself.
+//   TINY   |theta| < 2^-12       : (cos, sin) = (1, theta).
+// The operation sequences (and their host twins) are in sincosf_glibc.h.
+// Tiles that straddle ranges / binades / the period wrap take the generic per-sample routine.
+enum DirectRange { kRangeGeneric = 0, kRangeLarge = 1, kRangeMedium = 2, kRangeSmall = 3, kRangeTiny = 4 };
+
+// theta as the reference forms it (dsp.rs:121): f32(-2*PI) * (r * f32(n))
+__device__ __forceinline__ float theta_of(float r, uint32_t n)
+{
+    return __fmul_rn(__uint_as_float(0xC0C90FDBu), __fmul_rn(r, __uint2float_rn(n)));
+}
+
+// Range of a tile whose samplenum runs n_first .. n_last without wrapping.
+__device__ __forceinline__ int classify_tile(float r, uint32_t n_first, uint32_t n_last, db_window_t& t)
+{
+    const uint32_t b0 = __float_as_uint(theta_of(r, n_first)), b1 = __float_as_uint(theta_of(r, n_last));
+    const uint32_t a0 = b0 & 0x7fffffffu, a1 = b1 & 0x7fffffffu;
+    if (a0 > a1) return kRangeGeneric;   // cannot happen for finite r; NaN ordering is not relied on
+    if (a1 < 0x39800000u) return kRangeTiny;
+    if (a0 >= 0x39800000u && a1 < 0x3f400000u) return kRangeSmall;
+    if (a0 >= 0x3f400000u && a1 < 0x42f00000u) return kRangeMedium;
+    if (a0 >= 0x42f00000u && a1 < 0x7f800000u && (a0 >> 23) == (a1 >> 23)) {
+        db_large_window(b0, &t);
+        return kRangeLarge;
+    }
+    return kRangeGeneric;
+}
+
+template <int RANGE>
+__device__ __forceinline__ float2 phasor_fast(float theta, const db_window_t& t)
+{
+    float s = theta, c = 1.0f;   // kRangeTiny: sin = theta, cos = 1
+    if constexpr (RANGE == kRangeTiny) {
+    } else if constexpr (RANGE == kRangeSmall) {
+        db_sincosf_small(theta, &s, &c);
+    } else if constexpr (RANGE == kRangeMedium) {
+        db_sincosf_medium(theta, &s, &c);
+    } else {
+        db_sincosf_large(__float_as_uint(theta), &t, &s, &c);
+    }
+    return make_float2(c, s);
+}
+
+// Writes one lane's group of row u into the warp's output stage.
+template <typename C, int IN, int OUT>
+__device__ __forceinline__ void stage_group(unsigned char* out_s, int u, uint32_t lane, const float2 (&res)[C::G])
+{
+    unsigned char* dst = out_s + (u * 32 + lane) * C::kGroupOut;
+    if constexpr (OUT == I16 && C::G == 4) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(egress_i16_scaled<IN, OUT>(res[0]), egress_i16_scaled<IN, OUT>(res[1]),
+                                                    egress_i16_scaled<IN, OUT>(res[2]), egress_i16_scaled<IN, OUT>(res[3]));
+    } else if constexpr (OUT == I16) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(egress_i16(res[0]), egress_i16(res[1]));
+    } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(res[0].x, res[0].y, res[1].x, res[1].y);
+    }
+}
+
+// One full tile inside one piece, from the warp's shared-memory stage; phasors from a table.
 template <typename C, int IN, int OUT, int MODE>
 __device__ __forceinline__ void stream_tile(const uint32_t (&raw)[C::U][4], unsigned char* out_s, const DevPiece& p, uint32_t k0,
                                             const float2* tab, uint32_t plane_len, uint32_t lane)
 {
+    static_assert(MODE == kTabShared || MODE == kTabGlobal, "table modes only");
     constexpr int G = C::G, U = C::U;
     // phase index of the row's first sample (warp-uniform); lanes add G * lane
-    const uint32_t off0 = k0 - p.k_begin;
-    uint32_t j = 0;
-    if constexpr (MODE != kDirectLinear) j = piece_samplenum(p, off0) - 1u;
+    uint32_t j = piece_samplenum(p, k0 - p.k_begin) - 1u;
 #pragma unroll
     for (int u = 0; u < U; u++) {
         float2 smp[G], res[G];
@@ -475,28 +554,70 @@ __device__ __forceinline__ void stream_tile(const uint32_t (&raw)[C::U][4], unsi
             if constexpr (MODE == kTabShared) {
                 const uint32_t e = j + (uint32_t)s;                          // uniform part of the entry index
                 ph = tab[(e % G) * plane_len + e / G + lane];                // entry e + G*lane, plane (e mod G)
-            } else if constexpr (MODE == kTabGlobal) {
-                ph = __ldg(tab + wrap_phase(j + lane * G + (uint32_t)s, p.period));
-            } else if constexpr (MODE == kDirectPeriodic) {
-                ph = phasor(p.r, wrap_phase(j + lane * G + (uint32_t)s, p.period) + 1u);
             } else {
-                ph = phasor(p.r, p.base + off0 + (uint32_t)(u * C::kRow + s) + lane * G);
+                ph = __ldg(tab + wrap_phase(j + lane * G + (uint32_t)s, p.period));
             }
             res[s] = cmul_unfused(smp[s], ph);
         }
-        unsigned char* dst = out_s + (u * 32 + lane) * C::kGroupOut;
-        if constexpr (OUT == I16 && G == 4) {
-            *reinterpret_cast<uint4*>(dst) = make_uint4(egress_i16_scaled<IN, OUT>(res[0]), egress_i16_scaled<IN, OUT>(res[1]),
-                                                        egress_i16_scaled<IN, OUT>(res[2]), egress_i16_scaled<IN, OUT>(res[3]));
-        } else if constexpr (OUT == I16) {
-            *reinterpret_cast<uint2*>(dst) = make_uint2(egress_i16(res[0]), egress_i16(res[1]));
-        } else {
-            *reinterpret_cast<float4*>(dst) = make_float4(res[0].x, res[0].y, res[1].x, res[1].y);
-        }
-        if constexpr (MODE != kDirectLinear) {
-            j += p.step_u;
-            if (j >= p.period) j -= p.period;
-        }
+        stage_group<C, IN, OUT>(out_s, u, lane, res);
+        j += p.step_u;
+        if (j >= p.period) j -= p.period;
+    }
+}
+
+// All rows of a tile with the phasor of tile-relative sample i given by ph(i).
+template <typename C, int IN, int OUT, typename PH>
+__device__ __forceinline__ void stream_rows(const uint32_t (&raw)[C::U][4], unsigned char* out_s, uint32_t lane, PH ph)
+{
+    constexpr int G = C::G, U = C::U;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        float2 smp[G], res[G];
+        unpack_group<IN, OUT, G>(raw[u], smp);
+#pragma unroll
+        for (int s = 0; s < G; s++) res[s] = cmul_unfused(smp[s], ph(u * C::kRow + s));
+        stage_group<C, IN, OUT>(out_s, u, lane, res);
+    }
+}
+
+// One full tile inside one table-less piece (linear, or periodic without a table): direct evaluation.
+template <typename C, int IN, int OUT>
+__device__ __forceinline__ void stream_tile_direct(const uint32_t (&raw)[C::U][4], unsigned char* out_s, const DevPiece& p,
+                                                   uint32_t k0, uint32_t lane)
+{
+    constexpr uint32_t kTile = C::kTileSamples;
+    const uint32_t off0 = k0 - p.k_begin;
+    const float r = p.r;
+    uint32_t n0;   // samplenum of the tile's first sample
+    bool mono;     // samplenum runs n0, n0 + 1, ... through the whole tile (no period / u32 wrap)
+    if (p.period == 0) {
+        n0 = p.base + off0;
+        mono = n0 + (kTile - 1u) >= n0;
+    } else {
+        const uint32_t j = piece_samplenum(p, off0) - 1u;
+        n0 = j + 1u;
+        mono = j + kTile <= p.period;
+    }
+    db_window_t dt;
+    const int range = mono ? classify_tile(r, n0, n0 + (kTile - 1u), dt) : (int)kRangeGeneric;
+    const uint32_t nl = n0 + lane * C::G;   // this lane's first samplenum in row 0
+    if (range == kRangeLarge) {
+        stream_rows<C, IN, OUT>(raw, out_s, lane, [&](int i) { return phasor_fast<kRangeLarge>(theta_of(r, nl + (uint32_t)i), dt); });
+    } else if (range == kRangeMedium) {
+        stream_rows<C, IN, OUT>(raw, out_s, lane, [&](int i) { return phasor_fast<kRangeMedium>(theta_of(r, nl + (uint32_t)i), dt); });
+    } else if (range == kRangeSmall) {
+        stream_rows<C, IN, OUT>(raw, out_s, lane, [&](int i) { return phasor_fast<kRangeSmall>(theta_of(r, nl + (uint32_t)i), dt); });
+    } else if (range == kRangeTiny) {
+        stream_rows<C, IN, OUT>(raw, out_s, lane, [&](int i) { return phasor_fast<kRangeTiny>(theta_of(r, nl + (uint32_t)i), dt); });
+    } else if (p.period == 0) {
+        stream_rows<C, IN, OUT>(raw, out_s, lane, [&](int i) { return phasor(r, nl + (uint32_t)i); });
+    } else {
+        const uint32_t period = p.period;
+        stream_rows<C, IN, OUT>(raw, out_s, lane, [&](int i) {
+            uint32_t e = nl - 1u + (uint32_t)i;
+            if (e >= period) e %= period;
+            return phasor(r, e + 1u);
+        });
     }
 }
 
@@ -600,10 +721,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
             if (lane == 0) bulk_wait_read<S - 1>();   // the store that last read out[s] (tile i - S) has drained
             __syncwarp();
             if (lane == 0 && i + S < mine) issue_load(i + S);   // in[s] is in registers now: refill it
-            if (p.period == 0)
-                stream_tile<C, IN, OUT, kDirectLinear>(raw, out_s, p, k0, nullptr, 0, lane);
-            else if (p.tab == kNoTab)
-                stream_tile<C, IN, OUT, kDirectPeriodic>(raw, out_s, p, k0, nullptr, 0, lane);
+            if (p.tab == kNoTab)
+                stream_tile_direct<C, IN, OUT>(raw, out_s, p, k0, lane);
             else if (pi == a.smem_piece)
                 stream_tile<C, IN, OUT, kTabShared>(raw, out_s, p, k0, tab_s, plane_len, lane);
             else

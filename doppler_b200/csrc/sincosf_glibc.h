@@ -163,3 +163,113 @@ DB_HD db_sincos_t db_sincosf_glibc(float y)
     }
     return out;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Range-specialised evaluation: the same operation sequences as db_sincosf_glibc(), split by
+// glibc range for callers that already know (warp-uniformly) which range every argument of a
+// tile falls in (mixer_kernels.cuh, "Direct evaluation, fast rows").  No range branches, no
+// per-argument 4/pi window lookup, and on the device the double constants are read from the
+// constant bank as instruction operands instead of being re-materialised per use.
+//   db_sincosf_large : |y| >= 120, finite, all arguments of the tile in ONE binade.  glibc's
+//       reduce_large multiplies (m << shift) by a 96-bit window of 4/pi selected by the exponent;
+//       both depend only on the exponent, so the window is shifted once per tile
+//       (W = window << (e & 7), mod 2^96) and m * W == (m << shift) * window (mod 2^96), which is
+//       all that res0 = floor(product / 2^32) mod 2^64 keeps.
+//   db_sincosf_medium: 0.75 <= |y| < 120 (reduce_fast).
+//   db_sincosf_small : 2^-12 <= |y| < 0.75 (polynomial on y itself).
+// The host twins are checked against libm over every float of each range (tests/native).
+#define DB_KC_VALUES                                                                               \
+    0x1p0, -0x1.ffffffd0c621cp-2, 0x1.55553e1068f19p-5, -0x1.6c087e89a359dp-10,                   \
+    0x1.99343027bf8c3p-16, -0x1.555545995a603p-3, 0x1.1107605230bc4p-7, -0x1.994eb3774cf24p-13,   \
+    0x1.921fb54442d18p-62, 0x1.45f306dc9c883p+23, 0x1.921fb54442d18p+0
+// index:  0 C0  1 C1  2 C2  3 C3  4 C4  5 S1  6 S2  7 S3  8 pi*2^-63  9 2/pi*2^24  10 pi/2
+#if defined(__CUDACC__)
+__device__ __constant__ double db_kc_dev[11] = {DB_KC_VALUES};
+#endif
+#if !defined(__CUDA_ARCH__)
+static const double db_kc_host[11] = {DB_KC_VALUES};
+#endif
+#if defined(__CUDA_ARCH__)
+#define DB_K(i) db_kc_dev[i]
+#else
+#define DB_K(i) db_kc_host[i]
+#endif
+
+DB_HD void db_poly_fast(double xr, float* sp, float* cp)
+{
+    const double x2 = DB_DMUL(xr, xr);
+    const double x3 = DB_DMUL(x2, xr);
+    const double x4 = DB_DMUL(x2, x2);
+    const double c1 = DB_DFMA(x2, DB_K(1), DB_K(0));
+    const double s1 = DB_DFMA(x2, DB_K(7), DB_K(6));
+    const double c2 = DB_DFMA(x2, DB_K(4), DB_K(3));
+    const double x5 = DB_DMUL(x2, x3);
+    const double x6 = DB_DMUL(x2, x4);
+    const double s = DB_DFMA(x3, DB_K(5), xr);
+    const double c = DB_DFMA(x4, DB_K(2), c1);
+    *sp = DB_D2F(DB_DFMA(s1, x5, s));
+    *cp = DB_D2F(DB_DFMA(c2, x6, c));
+}
+
+struct db_window_t {
+    uint32_t w0, w1, w2;   // (4/pi window << (e & 7)) mod 2^96, most significant word first
+    uint32_t ks, kc;       // (sign + 1) << 30 and sign << 30, sign = (y < 0)
+};
+
+// Window and sign constants for every y that shares theta_bits' sign and exponent.
+DB_HD void db_large_window(uint32_t theta_bits, db_window_t* t)
+{
+    const uint32_t e = (theta_bits >> 23) & 0xffu, idx = (e >> 3) & 15u, sh = e & 7u;
+#if defined(__CUDA_ARCH__)
+    const uint32_t* arr = &db_inv_pio4_dev[idx];
+#else
+    const uint32_t* arr = &db_inv_pio4_host[idx];
+#endif
+    const uint32_t q0 = arr[0], q1 = arr[4], q2 = arr[8];
+    t->w0 = sh ? ((q0 << sh) | (q1 >> (32u - sh))) : q0;
+    t->w1 = sh ? ((q1 << sh) | (q2 >> (32u - sh))) : q1;
+    t->w2 = q2 << sh;
+    const uint32_t sign = theta_bits >> 31;
+    t->ks = (sign + 1u) << 30;
+    t->kc = sign << 30;
+}
+
+DB_HD void db_sincosf_large(uint32_t xi, const db_window_t* t, float* s, float* c)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t m;
+    asm("lop3.b32 %0, %1, 0x7fffff, 0x800000, 0xEA;" : "=r"(m) : "r"(xi));   // (xi & 0x7fffff) | 0x800000
+#else
+    const uint32_t m = (xi & 0x7fffffu) | 0x800000u;
+#endif
+    const uint32_t lo0 = m * t->w0;
+    const uint64_t p2 = (uint64_t)m * t->w2;
+    const uint64_t acc = (uint64_t)m * t->w1 + (((uint64_t)lo0 << 32) | (p2 >> 32));   // res0
+    const uint32_t hi = (uint32_t)(acc >> 32), lo = (uint32_t)acc;
+    const uint32_t q = hi + 0x20000000u;            // n = q >> 30
+    const uint32_t hi2 = hi - (q & 0xc0000000u);    // res0 - (n << 62)
+    const double xr = DB_DMUL(DB_LL2D((int64_t)(((uint64_t)hi2 << 32) | lo)), DB_K(8));
+    float sp, cp;
+    db_poly_fast(xr, &sp, &cp);
+    const uint32_t sb = DB_FBITS(sp) ^ ((q + t->ks) & 0x80000000u);   // (n + sign + 1) & 2
+    const uint32_t cb = DB_FBITS(cp) ^ ((q + t->kc) & 0x80000000u);   // (n + sign) & 2
+    const bool swap = (q & 0x40000000u) != 0;                         // n & 1
+    *s = DB_UBITS(swap ? cb : sb);
+    *c = DB_UBITS(swap ? sb : cb);
+}
+
+DB_HD void db_sincosf_medium(float y, float* s, float* c)
+{
+    const double x = DB_F2D(y);
+    const int32_t v = DB_D2I_RZ(DB_DMUL(x, DB_K(9))) + 0x800000;   // n = v >> 24 (arithmetic)
+    const double xr = DB_DFMA(-DB_I2D(v >> 24), DB_K(10), x);
+    float sp, cp;
+    db_poly_fast(xr, &sp, &cp);
+    const uint32_t sb = DB_FBITS(sp) ^ ((((uint32_t)v + 0x1000000u) << 6) & 0x80000000u);   // (n + 1) & 2
+    const uint32_t cb = DB_FBITS(cp) ^ (((uint32_t)v << 6) & 0x80000000u);                  // n & 2
+    const bool swap = ((uint32_t)v & 0x1000000u) != 0;                                      // n & 1
+    *s = DB_UBITS(swap ? cb : sb);
+    *c = DB_UBITS(swap ? sb : cb);
+}
+
+DB_HD void db_sincosf_small(float y, float* s, float* c) { db_poly_fast(DB_F2D(y), s, c); }

@@ -214,3 +214,41 @@ def test_device_phasor_matches_reference_ccexpf(oracle, mixer, shift, fs, n0, co
     assert same_bits_f32(s, s_ref) and same_bits_f32(c, c_ref)
     re, im = oracle.ccexpf(0.0, float(theta[count // 2]))
     assert np.float32(re).tobytes() == c[count // 2].tobytes() and np.float32(im).tobytes() == s[count // 2].tobytes()
+
+
+# (shift, fs, samplenum at the start, samples): table-less pieces, chosen so that whole tiles fall in each
+# glibc range of the direct-evaluation fast rows (mixer_kernels.cuh): LARGE with theta < 0 and > 0 and
+# several binade crossings, MEDIUM, SMALL, TINY, the f32(n) plateau above 2^24, the u32 wrap of
+# samplenum, a period wrap inside a table-less periodic piece, and |r| > 1.
+DIRECT_CASES = [
+    (4_000_000.5, 200_000_000, 0, 3_000_000),        # P = 4.9 M > samples: tiny -> small -> medium -> large
+    (-3_912_345.25, 200_000_000, 0, 50_000),         # P = 26 787, too short for a table: period wraps
+    (7321.7, 1_024_000, 0, 100_000),                 # P = 55 244, 1.8 periods: no table, theta < 0
+    (-9876.54, 1_024_000, 0, 200_000),               # P = 111 145: theta > 0, large range
+    (1.0, 2_000_000_000, 0, 2_000_000),              # never resets: tiny then small
+    (1.0, 2_000_000_000, 2**24 - 70_000, 300_000),   # f32(n) plateau
+    (3.0, 2_000_000_000, 2**32 - 100_000, 250_000),  # samplenum wraps to 0 (release-mode u32)
+    (1000.25, 48_000, 0, 150_000),                   # medium -> large within a few hundred samples
+    (123_456.7, 48_000, 5, 60_000),                  # |r| > 1: large from the second sample on
+    (-0.37, 1_000_000, 1_000_000, 400_000),          # small/medium boundary region
+]
+
+
+@pytest.mark.parametrize("shift,fs,sn0,n", DIRECT_CASES)
+def test_direct_fast_rows_match_oracle(oracle, mixer, shift, fs, sn0, n):
+    """Unit samples (1 + 0j) make the f32 output the phasor itself, so every bit of every sincosf result
+    of the direct path is compared with the reference's ccexpf; then random data through all type pairs."""
+    ones = np.zeros(2 * n, dtype=np.float32)
+    ones[0::2] = 1.0
+    got, sn = mixer.mix(ones.view(np.uint8), F32, F32, shift, fs, samplenum=sn0)
+    want, sn_ref = oracle.mix(ones.view(np.uint8), F32, F32, shift, fs, samplenum=sn0)
+    assert sn == sn_ref
+    check(oracle, got, want, F32)
+    rng = np.random.default_rng(n)
+    m = min(n, 300_000)
+    for intype, outtype in TYPE_PAIRS:
+        buf = make_input(rng, m, intype)
+        got, sn = mixer.mix(buf, intype, outtype, shift, fs, samplenum=sn0)
+        want, sn_ref = oracle.mix(buf, intype, outtype, shift, fs, samplenum=sn0)
+        assert sn == sn_ref
+        check(oracle, got, want, outtype)

@@ -16,6 +16,8 @@ def hostcheck():
     lib = ctypes.CDLL(os.path.join(ROOT, "tests", "native", "libhostcheck.so"))
     lib.hostcheck_sweep.restype = ctypes.c_uint64
     lib.hostcheck_sweep.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32)]
+    lib.hostcheck_fast_sweep.restype = ctypes.c_uint64
+    lib.hostcheck_fast_sweep.argtypes = lib.hostcheck_sweep.argtypes
     lib.hostcheck_sincosf.argtypes = [ctypes.c_float, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
     return lib
 
@@ -27,6 +29,21 @@ def test_strided_sweep_all_exponents(hostcheck):
     bad = ctypes.c_uint32(0)
     n = hostcheck.hostcheck_sweep(0, count, stride, os.cpu_count() or 1, ctypes.byref(bad))
     assert n == 0, f"{n} mismatches vs libm, e.g. bits 0x{bad.value:08x}"
+
+
+def test_range_specialised_twins_all_exponents(hostcheck):
+    """db_sincosf_large / _medium / _small (the direct-evaluation fast rows of the mixer kernel): every
+    pattern evaluated by the routine of its own glibc range, large-range window from its own exponent."""
+    full = os.environ.get("DOPPLER_FULL_SWEEP") == "1"
+    stride = 1 if full else 61
+    count = (2**32 + stride - 1) // stride
+    bad = ctypes.c_uint32(0)
+    n = hostcheck.hostcheck_fast_sweep(0, count, stride, os.cpu_count() or 1, ctypes.byref(bad))
+    assert n == 0, f"{n} mismatches vs libm, e.g. bits 0x{bad.value:08x}"
+    for centre in (0x39800000, 0x3F400000, 0x42F00000, 0x7F7FFFFF):   # range boundaries, both signs
+        for sign in (0, 0x80000000):
+            n = hostcheck.hostcheck_fast_sweep((centre - 200_000) | sign, 400_000, 1, 2, ctypes.byref(bad))
+            assert n == 0, hex(bad.value)
 
 
 def test_dense_around_branch_points(hostcheck):
