@@ -4,6 +4,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdoppler_b200.so")
+# tuning sweeps build variants of the library next to the product one (tools/tune); never a fallback
+if os.environ.get("DOPPLER_B200_LIB"):
+    LIB_PATH = os.path.abspath(os.environ["DOPPLER_B200_LIB"])
 
 c_ctx = ctypes.c_void_p
 u8p = ctypes.POINTER(ctypes.c_uint8)
@@ -56,6 +59,9 @@ SIGNATURES = {
                                                              ctypes.c_void_p]),
     "doppler_b200_plan_trace": (ctypes.c_long, [u32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32,
                                                 ctypes.c_uint64, ctypes.c_void_p]),
+    "doppler_b200_plan_tiles_trace": (ctypes.c_long, [ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
+                                                      ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32,
+                                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "doppler_b200_phasor_probe": (ctypes.c_int, [c_ctx, ctypes.c_float, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_void_p,
                                                  ctypes.c_void_p]),
     "doppler_b200_sincosf_probe": (ctypes.c_int, [c_ctx, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_size_t,

@@ -19,13 +19,44 @@
 #include "mixer_kernels.cuh"
 #include "plan.h"
 
+// (WARPS, S, U) of the segmented kernel per type pair, chosen on B200 (profiles/r01_seg_tune.md: warps
+// a multiple of the 4 schedulers, ~36-48 KB of loads in flight per SM, 12-16 samples per lane per tile so
+// that the per-tile pipeline overhead is amortised).  SEGV selects a tuning variant at build time
+// (`make variants`, tools/gpu_seg_tune.sh); the product is SEGV 0.
+#ifndef SEGV
+#define SEGV 0
+#endif
+#if SEGV == 1
+#define SEG_I16I16 16, 2, 4
+#define SEG_I16F32 12, 2, 4
+#define SEG_F32I16 16, 3, 3
+#define SEG_F32F32 24, 2, 2
+#elif SEGV == 2
+#define SEG_I16I16 12, 2, 5
+#define SEG_I16F32 12, 3, 5
+#define SEG_F32I16 20, 2, 4
+#define SEG_F32F32 20, 3, 2
+#elif SEGV == 3
+#define SEG_I16I16 8, 2, 6
+#define SEG_I16F32 8, 3, 6
+#define SEG_F32I16 12, 2, 4
+#define SEG_F32F32 12, 2, 4
+#else
+#define SEG_I16I16 12, 2, 4
+#define SEG_I16F32 12, 3, 4
+#define SEG_F32I16 20, 2, 3
+#define SEG_F32F32 20, 2, 2
+#endif
+
 using dmix::DevPiece;
+using dmix::DevSeg;
 using dmix::MixArgs;
 
 namespace {
 
 constexpr uint64_t kLaunchMaxSamples = 1ull << 30;   // k fits 32 bits with room for base + offset
-constexpr uint32_t kTabMaxPeriod = 1u << 22;         // 4 Mi entries = 32 MiB: stays L2-resident
+constexpr uint32_t kColumnMaxRows = 16;              // COLUMN segments: rows sharing one phasor evaluation, at most
+constexpr uint32_t kColumnMinRows = 2;               // fewer whole periods than this: evaluate per sample instead
 constexpr size_t kArenaMaxEntries = 64ull << 20;     // 512 MiB of (cos, sin) pairs
 constexpr uint32_t kSmemTabMaxEntries = 4096;        // 32 KiB of shared memory per CTA at most
 constexpr size_t kHostChunkBytes = 32ull << 20;      // host-path pipeline chunk (input side)
@@ -98,29 +129,42 @@ inline bool valid_type(int t) { return t == DOPPLER_B200_I16 || t == DOPPLER_B20
 
 using MixKernel = void (*)(const MixArgs);
 
-// The streaming kernel's shape per (intype, outtype): WARPS pipelines per CTA, S stages, U rows
-// per tile -- chosen on B200 with tools/tune (profiles/r01_tune_stream.md).
-struct StreamShape {
+// One kernel's shape: WARPS pipelines per CTA, S stages, U rows per tile (tools/tune, profiles/).
+struct KernShape {
     MixKernel kern;
     int warps;
-    uint32_t tile_samples, row_samples;
+    uint32_t tile_samples, row_samples, gran;
     uint32_t fixed_smem;
     uint32_t (*table_bytes)(uint32_t period);
 };
+// Per (intype, outtype): the lean loop for a launch that is one GRID segment (const mode), and the
+// segmented loop (GRID + COLUMN segments) with its own, larger tile.
+struct StreamShape {
+    KernShape grid, seg;
+};
 
-template <int IN, int OUT, int WARPS, int S, int U>
-StreamShape make_shape()
+template <int IN, int OUT, int WARPS, int S, int U, bool SEG>
+KernShape make_shape()
 {
     using C = dmix::StreamCfg<IN, OUT, WARPS, S, U>;
-    return StreamShape{dmix::mix_stream_kernel<IN, OUT, WARPS, S, U>, WARPS, (uint32_t)C::kTileSamples, (uint32_t)C::kRow,
-                       (uint32_t)C::kFixedSmem, &C::table_bytes};
+    return KernShape{SEG ? dmix::mix_stream_kernel<IN, OUT, WARPS, S, U> : dmix::mix_grid_kernel<IN, OUT, WARPS, S, U>, WARPS,
+                     (uint32_t)C::kTileSamples, (uint32_t)C::kRow, (uint32_t)C::kGran, (uint32_t)C::kFixedSmem, &C::table_bytes};
 }
+
+// (WARPS, S, U) of the segmented kernel per type pair; the host walk of the work decomposition
+// (doppler_b200_plan_tiles_trace) instantiates the same configurations.
+using SegI16I16 = dmix::StreamCfg<0, 0, SEG_I16I16>;
+using SegI16F32 = dmix::StreamCfg<0, 1, SEG_I16F32>;
+using SegF32I16 = dmix::StreamCfg<1, 0, SEG_F32I16>;
+using SegF32F32 = dmix::StreamCfg<1, 1, SEG_F32F32>;
 
 const StreamShape& shape_for(int in, int out)
 {
     static const StreamShape shapes[2][2] = {
-        {make_shape<0, 0, 20, 2, 2>(), make_shape<0, 1, 20, 3, 2>()},
-        {make_shape<1, 0, 16, 2, 3>(), make_shape<1, 1, 16, 2, 2>()},
+        {{make_shape<0, 0, 20, 2, 2, false>(), make_shape<0, 0, SEG_I16I16, true>()},
+         {make_shape<0, 1, 20, 3, 2, false>(), make_shape<0, 1, SEG_I16F32, true>()}},
+        {{make_shape<1, 0, 16, 2, 3, false>(), make_shape<1, 0, SEG_F32I16, true>()},
+         {make_shape<1, 1, 16, 2, 2, false>(), make_shape<1, 1, SEG_F32F32, true>()}},
     };
     return shapes[in][out];
 }
@@ -135,11 +179,13 @@ void magic_for(uint32_t d, uint32_t* magic, uint32_t* shift)
 }
 
 // Returns the arena offset of the phasor table for (r, period), building it on `s` if needed;
-// kNoTab when a table is not worthwhile or does not fit.
+// kNoTab when a table is not worthwhile.  Only periods that fit the kernel's shared-memory table
+// get one; longer periods are mixed as COLUMN segments (phasors evaluated once per column and
+// reused over rows) or, with fewer than kColumnMinRows whole periods, evaluated per sample.
 int get_table(doppler_b200_ctx* ctx, float r, uint32_t period, uint64_t piece_len, cudaStream_t s, uint32_t* off_out)
 {
     *off_out = dmix::kNoTab;
-    if (period > kTabMaxPeriod) return DOPPLER_B200_OK;
+    if (period > kSmemTabMaxEntries) return DOPPLER_B200_OK;
     uint32_t key;
     memcpy(&key, &r, 4);
     auto it = ctx->tables.find(key);
@@ -178,6 +224,155 @@ int get_table(doppler_b200_ctx* ctx, float r, uint32_t period, uint64_t piece_le
     return DOPPLER_B200_OK;
 }
 
+// Cuts one launch into segments (mixer_kernels.cuh, DevSeg): COLUMN for every table-less periodic
+// piece with at least kColumnMinRows whole periods, GRID everywhere else.  Returns tail_begin, the
+// granule-aligned end of the segmented range.  Host-only and device-free: exercised on the CPU by
+// doppler_b200_plan_tiles_trace (tests/test_plan.py).
+uint32_t build_segments(const std::vector<DevPiece>& dev, uint32_t nsamp, uint32_t T, uint32_t gran, uint32_t npipes,
+                        std::vector<DevSeg>* out)
+{
+    const uint32_t gmask = ~(gran - 1u), tail_begin = nsamp & gmask;
+    std::vector<DevSeg>& segs = *out;
+    for (uint32_t rcap = kColumnMaxRows;; rcap /= 2) {
+        segs.clear();
+        uint32_t cursor = 0, cursor_piece = 0, units = 0;
+        auto push_grid = [&](uint32_t b, uint32_t e, uint32_t piece) {
+            if (e <= b) return;
+            DevSeg g;
+            memset(&g, 0, sizeof g);
+            g.k_begin = b;
+            g.k_end = e;
+            g.piece = piece;
+            g.unit_begin = units;
+            units += (e - b + T - 1) / T;
+            g.unit_end = units;
+            segs.push_back(g);
+        };
+        for (size_t i = 0; i < dev.size() && rcap >= kColumnMinRows; i++) {
+            const DevPiece& d = dev[i];
+            if (d.period <= kSmemTabMaxEntries || d.tab != dmix::kNoTab) continue;
+            const uint64_t P = d.period, k_end = std::min<uint64_t>(d.k_end, tail_begin);
+            uint64_t k0 = (uint64_t)d.k_begin + (P - d.base) % P;                  // first sample with phase 0
+            if ((k0 & gmask) < std::max<uint64_t>(d.k_begin, cursor)) k0 += P;      // row 0 starts inside the piece, aligned
+            if (k0 >= k_end) continue;
+            const uint64_t rows = (k_end - k0) / P;
+            if (rows < kColumnMinRows) continue;
+            const uint32_t a_begin = (uint32_t)k0 & gmask, a_end = (uint32_t)(k0 + rows * P) & gmask;
+            push_grid(cursor, a_begin, cursor_piece);
+            DevSeg c;
+            memset(&c, 0, sizeof c);
+            c.k_begin = a_begin;
+            c.k_end = a_end;
+            c.piece = (uint32_t)i;
+            c.rows = (uint32_t)rows;
+            const uint32_t groups = ((uint32_t)rows + rcap - 1) / rcap;
+            c.rows_per_unit = ((uint32_t)rows + groups - 1) / groups;
+            c.ncols = (uint32_t)((P + gran - 1 + T - 1) / T);
+            magic_for(c.ncols, &c.ncols_magic, &c.ncols_shift);
+            c.k0 = (uint32_t)k0;
+            c.period = d.period;
+            c.unit_begin = units;
+            units += ((c.rows + c.rows_per_unit - 1) / c.rows_per_unit) * c.ncols;
+            c.unit_end = units;
+            segs.push_back(c);
+            cursor = a_end;
+            cursor_piece = (uint32_t)i;
+        }
+        push_grid(cursor, tail_begin, cursor_piece);
+        // fewer rows per unit (more, shorter units) until every pipeline has work
+        if (units >= npipes || rcap <= kColumnMinRows) break;
+    }
+    return tail_begin;
+}
+
+// Launch-relative device pieces of stream pieces clipped to [l0, l1) (tables not resolved: tab = kNoTab).
+void clip_pieces(const std::vector<dplan::Piece>& pieces, uint64_t l0, uint64_t l1, uint32_t row_samples,
+                 std::vector<DevPiece>* dev, std::vector<const dplan::Piece*>* src)
+{
+    for (size_t i = 0; i < pieces.size(); i++) {
+        const dplan::Piece& pc = pieces[i];
+        if (pc.k_end <= l0 || pc.k_begin >= l1) continue;
+        const uint64_t b = std::max(pc.k_begin, l0), e = std::min(pc.k_end, l1);
+        const uint64_t delta = b - pc.k_begin;
+        DevPiece d;
+        memset(&d, 0, sizeof d);
+        d.k_begin = (uint32_t)(b - l0);
+        d.k_end = (uint32_t)(e - l0);
+        d.period = pc.period;
+        d.r = pc.r;
+        d.tab = dmix::kNoTab;
+        if (pc.period == 0) {
+            d.base = pc.base + (uint32_t)delta;
+        } else {
+            d.base = (uint32_t)(((uint64_t)pc.base + delta) % pc.period);
+            magic_for(pc.period, &d.magic, &d.shift);
+            d.step_u = row_samples % pc.period;
+        }
+        dev->push_back(d);
+        if (src) src->push_back(&pc);
+    }
+}
+
+// Host walk of one launch's work decomposition (doppler_b200_plan_tiles_trace).
+template <typename C>
+long tiles_trace(const std::vector<DevPiece>& dev, uint32_t nsamp, uint32_t npipes, uint32_t* trace, uint32_t* cover,
+                 uint64_t* stats)
+{
+    std::vector<DevSeg> segs;
+    const uint32_t tail_begin = build_segments(dev, nsamp, (uint32_t)C::kTileSamples, (uint32_t)C::kGran, npipes, &segs);
+    MixArgs a;
+    memset(&a, 0, sizeof a);
+    a.nsamples = nsamp;
+    a.npieces = (uint32_t)dev.size();
+    a.pieces = dev.data();
+    a.nsegs = (uint32_t)segs.size();
+    a.segs = segs.data();
+    for (size_t i = 0; i < segs.size() && i < (size_t)dmix::kInlineSegs; i++) a.inl_segs[i] = segs[i];
+    a.nunits = segs.empty() ? 0 : segs.back().unit_end;
+    a.tail_begin = tail_begin;
+    uint64_t ncol = 0, ntiles = 0;
+    for (const DevSeg& g : segs) ncol += g.rows != 0;
+    for (uint32_t pipe = 0; pipe < npipes; pipe++) {
+        dmix::TileIter<C> it;
+        it.init(a, pipe, npipes);
+        dmix::TileDesc d;
+        size_t pi = 0;
+        while (it.next(a, d)) {
+            ntiles++;
+            if (d.nsamp == 0 || d.nsamp > (uint32_t)C::kTileSamples || (d.k0 | d.nsamp) % C::kGran) return -2;
+            for (uint32_t x = 0; x < d.nsamp; x++) {
+                const uint32_t k = d.k0 + x;
+                if (k >= nsamp) return -3;
+                uint32_t n;
+                if (d.info & dmix::kColFlag) {
+                    // the kernel's COLUMN arithmetic: window entry x + kWinLead - s_j of the window that
+                    // starts at phase phase0 - kWinLead (mod period)
+                    const DevSeg& g = segs[d.seg];
+                    const uint32_t e = x + dmix::kWinLead - (d.info & 0xffu);
+                    const uint32_t f0 = d.phase0 >= (uint32_t)dmix::kWinLead ? d.phase0 - dmix::kWinLead
+                                                                              : d.phase0 + g.period - dmix::kWinLead;
+                    n = (uint32_t)(((uint64_t)f0 + e) % g.period) + 1u;
+                } else {
+                    while (pi + 1 < dev.size() && k >= dev[pi].k_end) pi++;
+                    while (pi > 0 && k < dev[pi].k_begin) pi--;
+                    const DevPiece& p = dev[pi];
+                    const uint32_t off = k - p.k_begin;
+                    n = p.period ? (uint32_t)(((uint64_t)p.base + off) % p.period) + 1u : p.base + off;
+                }
+                trace[k] = n;
+                cover[k]++;
+            }
+        }
+    }
+    if (stats) {
+        stats[0] = segs.size();
+        stats[1] = ncol;
+        stats[2] = a.nunits;
+        stats[3] = ntiles;
+    }
+    return (long)tail_begin;
+}
+
 // Enqueues the mixer over device buffers for a list of constant-shift runs.
 int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t nsamples, int intype, int outtype,
                const std::vector<dplan::Run>& runs, uint32_t* samplenum, cudaStream_t s)
@@ -186,41 +381,26 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
     std::vector<dplan::Piece> pieces;
     ctx->planner.plan(runs, 0, samplenum, &pieces);
 
-    const StreamShape& shape = shape_for(intype, outtype);
+    const StreamShape& shapes = shape_for(intype, outtype);
     const size_t ibps = bytes_per_sample(intype), obps = bytes_per_sample(outtype);
-    // launches are cut at tile boundaries so that every launch but the last has no ragged tail
-    const uint64_t launch_max = kLaunchMaxSamples / shape.tile_samples * shape.tile_samples;
+    // launches are cut at a common multiple of both kernels' tiles so that every launch but the last has no ragged tail
+    const uint64_t lcm_tile = (uint64_t)shapes.grid.tile_samples * shapes.seg.tile_samples;
+    const uint64_t launch_max = kLaunchMaxSamples / lcm_tile * lcm_tile;
 
     if (ctx->tables_event_valid) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->tables_ready, 0));
 
-    size_t first_piece = 0;
     for (uint64_t l0 = 0; l0 < nsamples; l0 += launch_max) {
         const uint64_t l1 = std::min(nsamples, l0 + launch_max);
         std::vector<DevPiece> dev;
+        std::vector<const dplan::Piece*> src;
         std::vector<uint64_t> dev_len;
-        while (first_piece < pieces.size() && pieces[first_piece].k_end <= l0) first_piece++;
-        for (size_t i = first_piece; i < pieces.size() && pieces[i].k_begin < l1; i++) {
-            const dplan::Piece& pc = pieces[i];
-            const uint64_t b = std::max(pc.k_begin, l0), e = std::min(pc.k_end, l1);
-            const uint64_t delta = b - pc.k_begin;
-            DevPiece d;
-            memset(&d, 0, sizeof d);
-            d.k_begin = (uint32_t)(b - l0);
-            d.k_end = (uint32_t)(e - l0);
-            d.period = pc.period;
-            d.r = pc.r;
-            d.tab = dmix::kNoTab;
-            if (pc.period == 0) {
-                d.base = pc.base + (uint32_t)delta;
-            } else {
-                d.base = (uint32_t)(((uint64_t)pc.base + delta) % pc.period);
-                magic_for(pc.period, &d.magic, &d.shift);
-                d.step_u = shape.row_samples % pc.period;
-                int rc = get_table(ctx, pc.r, pc.period, pc.k_end - pc.k_begin, s, &d.tab);
+        clip_pieces(pieces, l0, l1, shapes.grid.row_samples, &dev, &src);
+        for (size_t i = 0; i < dev.size(); i++) {
+            dev_len.push_back(dev[i].k_end - dev[i].k_begin);
+            if (dev[i].period) {
+                int rc = get_table(ctx, dev[i].r, dev[i].period, src[i]->k_end - src[i]->k_begin, s, &dev[i].tab);
                 if (rc) return rc;
             }
-            dev.push_back(d);
-            dev_len.push_back(e - b);
         }
         // get_table may have recycled the arena: offsets taken earlier in this launch would
         // dangle.  Re-resolve every tabled piece against the final cache (cheap, rare).
@@ -240,16 +420,27 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
             }
         }
 
+        const uint32_t nsamp = (uint32_t)(l1 - l0);
+        std::vector<DevSeg> segs;
+        const uint32_t tail_begin = build_segments(dev, nsamp, shapes.seg.tile_samples, shapes.seg.gran,
+                                                   (uint32_t)ctx->sm_count * (uint32_t)shapes.seg.warps, &segs);
+        // no COLUMN segment: the whole launch is one GRID segment and takes the lean loop
+        const bool grid_only = segs.size() <= 1 && (segs.empty() || segs[0].rows == 0);
+        const KernShape& shape = grid_only ? shapes.grid : shapes.seg;
+
         MixArgs a;
         memset(&a, 0, sizeof a);
         a.in = static_cast<const char*>(d_in) + l0 * ibps;
         a.out = static_cast<char*>(d_out) + l0 * obps;
         a.tables = ctx->arena;
-        a.nsamples = (uint32_t)(l1 - l0);
+        a.nsamples = nsamp;
         a.npieces = (uint32_t)dev.size();
-        a.ntiles = a.nsamples / shape.tile_samples;   // full tiles; the ragged end is mixed from global memory
+        a.nsegs = (uint32_t)segs.size();
+        a.nunits = segs.empty() ? 0 : segs.back().unit_end;
+        a.tail_begin = tail_begin;
         a.smem_piece = smem_piece;
         DevPiece* d_pieces = nullptr;
+        DevSeg* d_segs = nullptr;
         if (dev.size() <= (size_t)dmix::kInlinePieces) {
             for (size_t i = 0; i < dev.size(); i++) a.inl[i] = dev[i];
         } else {
@@ -257,13 +448,22 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
             CUDA_TRY(ctx, cudaMemcpyAsync(d_pieces, dev.data(), dev.size() * sizeof(DevPiece), cudaMemcpyHostToDevice, s));
             a.pieces = d_pieces;
         }
-        // persistent: one CTA per SM, every warp an independent pipeline over interleaved tiles
-        const uint32_t want = (a.ntiles + shape.warps - 1) / shape.warps;
+        if (segs.size() <= (size_t)dmix::kInlineSegs) {
+            for (size_t i = 0; i < segs.size(); i++) a.inl_segs[i] = segs[i];
+        } else {
+            CUDA_TRY(ctx, cudaMallocAsync(&d_segs, segs.size() * sizeof(DevSeg), s));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(DevSeg), cudaMemcpyHostToDevice, s));
+            a.segs = d_segs;
+        }
+        // persistent: one CTA per SM, every warp an independent pipeline over interleaved work units
+        if (grid_only) a.nunits = nsamp / shape.tile_samples;   // whole tiles; the lean loop mixes the ragged end itself
+        const uint32_t want = (a.nunits + shape.warps - 1) / shape.warps;
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->sm_count, want));
         const size_t smem = shape.fixed_smem + (smem_piece != dmix::kNoPiece ? shape.table_bytes(dev[smem_piece].period) : 0);
         shape.kern<<<grid, shape.warps * 32, smem, s>>>(a);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
+        if (d_segs) CUDA_TRY(ctx, cudaFreeAsync(d_segs, s));
         if (d_pieces) CUDA_TRY(ctx, cudaFreeAsync(d_pieces, s));
     }
     return DOPPLER_B200_OK;
@@ -434,8 +634,10 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     for (int i = 0; i < 2 && e2 == cudaSuccess; i++)
         for (int o = 0; o < 2 && e2 == cudaSuccess; o++) {
             const StreamShape& sh = shape_for(i, o);
-            e2 = cudaFuncSetAttribute(sh.kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sh.fixed_smem + sh.table_bytes(kSmemTabMaxEntries)));
+            for (const KernShape* k : {&sh.grid, &sh.seg})
+                if (e2 == cudaSuccess)
+                    e2 = cudaFuncSetAttribute(k->kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(k->fixed_smem + k->table_bytes(kSmemTabMaxEntries)));
         }
     if (e2 != cudaSuccess) {
         fail(nullptr, DOPPLER_B200_ECUDA, "context setup failed: %s", cudaGetErrorString(e2));
@@ -636,6 +838,24 @@ long doppler_b200_plan_trace(uint32_t* samplenum, const float* shifts, size_t nb
             }
     }
     return (long)pieces.size();
+}
+
+long doppler_b200_plan_tiles_trace(int intype, int outtype, uint32_t samplenum, const float* shifts, size_t nblocks,
+                                   uint64_t block_samples, uint32_t samplerate, uint64_t count, uint32_t npipes,
+                                   uint32_t* trace, uint32_t* cover, uint64_t* stats)
+{
+    if (!valid_type(intype) || !valid_type(outtype) || !shifts || nblocks == 0 || block_samples == 0 || !trace || !cover ||
+        npipes == 0 || count == 0 || count > kLaunchMaxSamples)
+        return -1;
+    dplan::Planner pl;
+    std::vector<dplan::Piece> pieces;
+    pl.plan(dplan::runs_from_blocks(shifts, nblocks, block_samples, samplerate, count), 0, &samplenum, &pieces);
+    std::vector<DevPiece> dev;
+    clip_pieces(pieces, 0, count, shape_for(intype, outtype).seg.row_samples, &dev, nullptr);
+    if (intype == DOPPLER_B200_I16 && outtype == DOPPLER_B200_I16) return tiles_trace<SegI16I16>(dev, (uint32_t)count, npipes, trace, cover, stats);
+    if (intype == DOPPLER_B200_I16) return tiles_trace<SegI16F32>(dev, (uint32_t)count, npipes, trace, cover, stats);
+    if (outtype == DOPPLER_B200_I16) return tiles_trace<SegF32I16>(dev, (uint32_t)count, npipes, trace, cover, stats);
+    return tiles_trace<SegF32F32>(dev, (uint32_t)count, npipes, trace, cover, stats);
 }
 
 // ---- device self-test probes ------------------------------------------------------------------

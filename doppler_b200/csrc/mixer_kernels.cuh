@@ -60,25 +60,71 @@ struct DevPiece {          // launch-relative sample indices
 };
 static_assert(sizeof(DevPiece) == 48, "DevPiece layout");
 
+// A launch is cut into SEGMENTS of two kinds (all sample indices launch-relative; segment bounds
+// are multiples of the alignment granule, so every bulk copy is 16-byte aligned):
+//   GRID    contiguous tiles of kTileSamples, one work unit per tile; may contain any pieces.
+//   COLUMN  `rows` whole periods of ONE periodic piece whose table does not fit shared memory.
+//           Row j starts at a_j = align_down(k0 + j * period).  A work unit is one column tile c
+//           (phases c*T - s_j ... of every row) over `rows_per_unit` consecutive rows: the warp
+//           evaluates the column's phasors ONCE (direct, bit-exact sincosf), parks them in shared
+//           memory and reuses them for every row, so evaluation cost per sample drops by the
+//           number of rows.  s_j = (k0 + j*period) - a_j (0 .. granule-1) is the row's phase shift.
+struct DevSeg {
+    uint32_t unit_begin, unit_end;   // work units [unit_begin, unit_end)
+    uint32_t k_begin, k_end;         // samples [k_begin, k_end)
+    uint32_t piece;                  // GRID: piece containing k_begin; COLUMN: the periodic piece
+    uint32_t rows;                   // COLUMN: whole periods covered; 0 -> GRID
+    uint32_t rows_per_unit;          // COLUMN: rows sharing one phasor evaluation
+    uint32_t ncols;                  // COLUMN: column tiles per row
+    uint32_t ncols_magic, ncols_shift;   // division by ncols (x < 2^31)
+    uint32_t k0;                     // COLUMN: sample holding phase 0 of row 0
+    uint32_t period;                 // COLUMN: copy of the piece's period
+};
+static_assert(sizeof(DevSeg) == 48, "DevSeg layout");
+
+constexpr int kInlineSegs = 3;
+
+// One tile of work, produced by lane 0's iterator when it issues the tile's bulk load and read
+// back by the whole warp when the tile reaches the compute stage.
+struct TileDesc {
+    uint32_t k0;       // first sample
+    uint32_t nsamp;    // samples (granule multiple, <= kTileSamples); 0 = end of this warp's work
+    uint32_t seg;      // segment index
+    uint32_t info;     // COLUMN: kColFlag | kColFirst (evaluate the phasor window) | row shift s_j
+    uint32_t phase0;   // COLUMN: phase of the column's first sample (c * kTileSamples)
+    uint32_t pad[3];
+};
+static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
+constexpr uint32_t kColFlag = 0x80000000u, kColFirst = 0x40000000u;
+constexpr int kWinLead = 3;   // window entries ahead of the column's first phase (largest row shift)
+
 struct MixArgs {
     const void* in;
     void* out;
     const DevPiece* pieces;   // global copy when npieces > kInlinePieces
+    const DevSeg* segs;       // global copy when nsegs > kInlineSegs
     const float2* tables;     // phasor arena: entry = (cos, sin)
     uint32_t nsamples;
     uint32_t npieces;
-    uint32_t ntiles;
-    uint32_t tiles_per_cta;
-    uint32_t smem_entries;    // capacity of the shared-memory table (excluding pad)
-    uint32_t interleave;      // 0: CTA b owns tiles [b*tiles_per_cta, (b+1)*tiles_per_cta); 1: tiles b, b+grid, ...
+    uint32_t nsegs;
+    uint32_t nunits;          // work units over all segments
+    uint32_t tail_begin;      // samples [tail_begin, nsamples): the sub-granule end of the buffer
+    uint32_t ntiles;          // mix_kernel (tuning harness) only
+    uint32_t tiles_per_cta;   // mix_kernel only
+    uint32_t smem_entries;    // mix_kernel only
+    uint32_t interleave;      // mix_kernel only
     uint32_t smem_piece;      // streaming kernel: piece whose table is staged in shared memory, or kNoPiece
     DevPiece inl[kInlinePieces];
+    DevSeg inl_segs[kInlineSegs];
 };
 
 // ---------------------------------------------------------------------------------------------
 // phasor: ccexpf(0 + i*theta), theta = (-2*PI) * (r * f32(n))   (dsp.rs:121-122, complex.c:33-39)
 // For a zero real part glibc's cexpf is exp(0)=1 times sincosf(theta); non-finite theta -> NaN.
-__device__ __forceinline__ float2 phasor(float r, uint32_t n)
+// Deliberately NOT inlined: this is the generic (any-range) routine of the rare paths -- tiles that
+// straddle pieces / ranges / period wraps, table builds, probes; the hot paths use tables or the
+// range-specialised rows below.  One shared copy keeps the kernels inside the instruction cache.
+__device__ __noinline__ float2 phasor(float r, uint32_t n)
 {
     const float x = __fmul_rn(r, __uint2float_rn(n));
     const float theta = __fmul_rn(__uint_as_float(0xC0C90FDBu) /* -2.0f * PI_f32 */, x);
@@ -405,7 +451,16 @@ struct StreamCfg {
     static constexpr int kTileOut = 32 * U * kGroupOut;
     static constexpr int kRing = S * (kTileIn + kTileOut);  // per warp
     static constexpr int kBarBytes = ((WARPS * S * 8 + 127) / 128) * 128;
-    static constexpr int kFixedSmem = kBarBytes + WARPS * kRing;
+    static constexpr int kDescBytes = S * (int)sizeof(TileDesc);   // per warp
+    // alignment granule in samples: both sides of every bulk copy must be 16-byte granular
+    static constexpr int kGran = (IN == I16 || OUT == I16) ? 4 : 2;
+    // COLUMN phasor window: kWinIters entries per lane cover phases c*T - kWinLead .. c*T + T;
+    // G planes (entry e -> plane e mod G) of kWinPlane float2, kWinPlane = 16/G (mod 16) so that
+    // the lane-consecutive 64-bit stores of the evaluation pass are bank-conflict free.
+    static constexpr int kWinIters = (kTileSamples + kWinLead + 1 + 31) / 32;
+    static constexpr int kWinPlane = ((32 * kWinIters / G + 15) / 16) * 16 + 16 / G;
+    static constexpr int kWinBytes = G * kWinPlane * 8;            // per warp
+    static constexpr int kFixedSmem = kBarBytes + WARPS * (kRing + kDescBytes + kWinBytes);
     // shared-memory table: G planes of plane_len(entries) float2 each
     __host__ __device__ static constexpr uint32_t plane_len(uint32_t period) { return (period + kRow + G - 1) / G + 1; }
     __host__ __device__ static constexpr uint32_t table_bytes(uint32_t period) { return G * plane_len(period) * 8; }
@@ -621,13 +676,13 @@ __device__ __forceinline__ void stream_tile_direct(const uint32_t (&raw)[C::U][4
     }
 }
 
-// A full tile that straddles pieces: per-sample piece lookup and direct phasor, still staged.
+// A tile that straddles pieces: per-sample piece lookup and generic phasor, still staged.
 template <typename C, int IN, int OUT>
 __device__ __noinline__ void stream_tile_slow(const MixArgs& a, uint32_t pi, const unsigned char* in_s, unsigned char* out_s,
-                                              uint32_t k0, uint32_t lane)
+                                              uint32_t k0, uint32_t nsamp, uint32_t lane)
 {
     DevPiece p = get_piece(a, pi);
-    for (uint32_t i = lane; i < (uint32_t)C::kTileSamples; i += 32) {
+    for (uint32_t i = lane; i < nsamp; i += 32) {
         const uint32_t k = k0 + i;
         if (k >= p.k_end) {
             pi = find_piece(a, pi, k);
@@ -647,8 +702,284 @@ __device__ __noinline__ void stream_tile_slow(const MixArgs& a, uint32_t pi, con
     }
 }
 
+__host__ __device__ __forceinline__ DevSeg get_seg(const MixArgs& a, uint32_t i)
+{
+    if (a.nsegs <= (uint32_t)kInlineSegs) return a.inl_segs[i];
+    return a.segs[i];
+}
+
+// COLUMN: evaluate the phasor window of one column into the warp's planes.  Entry e holds the
+// phasor of phase (phase0 - kWinLead + e) mod period, i.e. samplenum = that + 1.
+template <typename C>
+__device__ __forceinline__ void eval_window(float2* win, float r, uint32_t period, uint32_t phase0, uint32_t lane)
+{
+    constexpr int G = C::G, NW = C::kWinIters, PL = C::kWinPlane;
+    // phase of entry 0; only column 0 reaches back into the previous period
+    const uint32_t f0 = phase0 >= (uint32_t)kWinLead ? phase0 - kWinLead : phase0 + period - kWinLead;
+    const bool mono = f0 + 32u * NW <= period;   // no period wrap inside the window
+    db_window_t dt;
+    const int range = mono ? classify_tile(r, f0 + 1u, f0 + 32u * NW, dt) : (int)kRangeGeneric;
+    float2* dst = win + (lane % G) * PL + lane / G;   // entry e = lane + 32*it -> plane e % G, slot e / G
+    const uint32_t nl = f0 + 1u + lane;
+    if (range == kRangeLarge) {
+#pragma unroll 3
+        for (int it = 0; it < NW; it++) dst[it * (32 / G)] = phasor_fast<kRangeLarge>(theta_of(r, nl + 32u * it), dt);
+    } else if (range == kRangeMedium) {
+#pragma unroll 3
+        for (int it = 0; it < NW; it++) dst[it * (32 / G)] = phasor_fast<kRangeMedium>(theta_of(r, nl + 32u * it), dt);
+    } else if (range == kRangeSmall) {
+#pragma unroll 3
+        for (int it = 0; it < NW; it++) dst[it * (32 / G)] = phasor_fast<kRangeSmall>(theta_of(r, nl + 32u * it), dt);
+    } else if (range == kRangeTiny) {
+#pragma unroll 3
+        for (int it = 0; it < NW; it++) dst[it * (32 / G)] = phasor_fast<kRangeTiny>(theta_of(r, nl + 32u * it), dt);
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < NW; it++) {
+            uint32_t f = f0 + lane + 32u * it;
+            if (f >= period) f -= period;
+            if (f >= period) f %= period;
+            dst[it * (32 / G)] = phasor(r, f + 1u);
+        }
+    }
+}
+
+// COLUMN: one row tile against the parked window; sh = the row's phase shift s_j.
+template <typename C, int IN, int OUT>
+__device__ __forceinline__ void stream_tile_column(const uint32_t (&raw)[C::U][4], unsigned char* out_s, const float2* win,
+                                                   uint32_t sh, uint32_t lane)
+{
+    constexpr int G = C::G, U = C::U, PL = C::kWinPlane;
+    constexpr int LOGG = G == 4 ? 2 : 1;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        float2 smp[G], res[G];
+        unpack_group<IN, OUT, G>(raw[u], smp);
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            // sample u*32G + G*lane + g has phase phase0 + that - sh -> window entry that + kWinLead - sh
+            const uint32_t x = (uint32_t)(g + kWinLead) - sh;                     // warp-uniform, 0 .. G + 2
+            const float2 ph = win[(x & (G - 1)) * PL + (x >> LOGG) + u * 32 + lane];
+            res[g] = cmul_unfused(smp[g], ph);
+        }
+        stage_group<C, IN, OUT>(out_s, u, lane, res);
+    }
+}
+
+// Lane 0's work iterator: expands this pipeline's work units (pipe, pipe + npipes, ...) into tiles.
+template <typename C>
+struct TileIter {
+    uint32_t u, step, nunits;
+    uint32_t seg;
+    DevSeg sg;
+    uint32_t c, j, jend;
+    bool first, started;
+
+    __host__ __device__ __forceinline__ void init(const MixArgs& a, uint32_t pipe, uint32_t npipes)
+    {
+        u = pipe;
+        step = npipes;
+        nunits = a.nunits;
+        seg = 0;
+        sg = get_seg(a, 0);
+        c = j = jend = 0;
+        first = started = false;
+    }
+
+    __host__ __device__ __forceinline__ bool next(const MixArgs& a, TileDesc& d)
+    {
+        constexpr uint32_t T = C::kTileSamples, GM = ~(uint32_t)(C::kGran - 1);
+        for (;;) {
+            if (j < jend) {   // rows left in the current column unit
+                const uint32_t kj = sg.k0 + j * sg.period;
+                const uint32_t aj = kj & GM, aj1 = (kj + sg.period) & GM;
+                const uint32_t start = aj + c * T;
+                j++;
+                if (start >= aj1) continue;   // this row is a few samples shorter than the last column
+                d.k0 = start;
+                d.nsamp = aj1 - start < T ? aj1 - start : T;
+                d.seg = seg;
+                d.info = kColFlag | (first ? kColFirst : 0u) | (kj - aj);
+                d.phase0 = c * T;
+                first = false;
+                return true;
+            }
+            if (started) u += step;
+            started = true;
+            if (u >= nunits) return false;
+            while (u >= sg.unit_end) sg = get_seg(a, ++seg);
+            const uint32_t v = u - sg.unit_begin;
+            if (sg.rows == 0) {
+                const uint32_t start = sg.k_begin + v * T;
+                d.k0 = start;
+                d.nsamp = sg.k_end - start < T ? sg.k_end - start : T;
+                d.seg = seg;
+                d.info = 0;
+                d.phase0 = 0;
+                return true;
+            }
+            const uint32_t g = (uint32_t)(((uint64_t)v * sg.ncols_magic) >> sg.ncols_shift);
+            c = v - g * sg.ncols;
+            j = g * sg.rows_per_unit;
+            jend = j + sg.rows_per_unit < sg.rows ? j + sg.rows_per_unit : sg.rows;
+            first = true;
+        }
+    }
+};
+
 template <int IN, int OUT, int WARPS, int S, int U>
 __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_constant__ MixArgs a)
+{
+    using C = StreamCfg<IN, OUT, WARPS, S, U>;
+    constexpr int G = C::G;
+    constexpr uint32_t kInBps = IN == I16 ? 4 : 8, kOutBps = OUT == I16 ? 4 : 8;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    unsigned char* rings = smem + C::kBarBytes;
+    unsigned char* descs = rings + WARPS * C::kRing;
+    unsigned char* wins = descs + WARPS * C::kDescBytes;
+    float2* tab_s = reinterpret_cast<float2*>(smem + C::kFixedSmem);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* full = bars + warp * S;
+    unsigned char* ring_in = rings + warp * C::kRing;
+    unsigned char* ring_out = ring_in + S * C::kTileIn;
+    TileDesc* desc_ring = reinterpret_cast<TileDesc*>(descs + warp * C::kDescBytes);
+    float2* win = reinterpret_cast<float2*>(wins + warp * C::kWinBytes);
+
+    // start-up: barriers + (optionally) one piece's table de-interleaved into shared memory
+    uint32_t plane_len = 0;
+    if (a.smem_piece != kNoPiece) {
+        const DevPiece sp = get_piece(a, a.smem_piece);
+        plane_len = C::plane_len(sp.period);
+        const float2* src = a.tables + sp.tab;
+        for (uint32_t e = threadIdx.x; e < sp.period + (uint32_t)C::kRow; e += WARPS * 32)
+            tab_s[(e % G) * plane_len + e / G] = __ldg(src + e % sp.period);   // replicated past the period: no wrap in a row
+    }
+    if (lane == 0) {
+        for (int s = 0; s < S; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t pipe = blockIdx.x * WARPS + warp, npipes = gridDim.x * WARPS;
+    const unsigned char* gin = static_cast<const unsigned char*>(a.in);
+    unsigned char* gout = static_cast<unsigned char*>(a.out);
+
+    // lane 0: iterator + load issue; the descriptor travels to the compute stage through shared memory
+    TileIter<C> it;
+    it.init(a, pipe, npipes);
+    auto issue_next = [&](uint32_t s) {   // lane 0 only
+        TileDesc d;
+        if (it.next(a, d)) {
+            const uint32_t bytes = d.nsamp * kInBps;
+            mbar_expect_tx(&full[s], bytes);
+            bulk_g2s(ring_in + s * C::kTileIn, gin + (size_t)d.k0 * kInBps, bytes, &full[s]);
+        } else {
+            d.k0 = d.nsamp = d.seg = d.info = d.phase0 = 0;
+        }
+        desc_ring[s] = d;
+    };
+    if (lane == 0)
+        for (uint32_t s = 0; s < (uint32_t)S; s++) issue_next(s);
+
+    uint32_t pi = 0;                 // GRID: cached piece
+    DevPiece p = get_piece(a, 0);
+    uint32_t cseg = 0xffffffffu;     // COLUMN: cached segment -> its piece's r / period
+    float col_r = 0.0f;
+    uint32_t col_period = 1;
+    for (uint32_t i = 0;; i++) {
+        const uint32_t s = i % S;
+        __syncwarp();
+        const TileDesc d = desc_ring[s];
+        if (d.nsamp == 0) break;
+        const unsigned char* in_s = ring_in + s * C::kTileIn;
+        unsigned char* out_s = ring_out + s * C::kTileOut;
+        mbar_wait(&full[s], (i / S) & 1u);
+        uint32_t raw[U][4];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned char* src = in_s + (u * 32 + lane) * C::kGroupIn;
+            if constexpr (C::kGroupIn == 16) {
+                const uint4 w = *reinterpret_cast<const uint4*>(src);
+                raw[u][0] = w.x, raw[u][1] = w.y, raw[u][2] = w.z, raw[u][3] = w.w;
+            } else {
+                const uint2 w = *reinterpret_cast<const uint2*>(src);
+                raw[u][0] = w.x, raw[u][1] = w.y, raw[u][2] = 0, raw[u][3] = 0;
+            }
+        }
+        if (lane == 0) bulk_wait_read<S - 1>();   // the store that last read out[s] (tile i - S) has drained
+        __syncwarp();                              // in[s] and desc[s] are in registers now
+        bool refilled = false;
+        if (d.info & kColFlag) {
+            if (lane == 0) issue_next(s);
+            refilled = true;
+            if (d.seg != cseg) {
+                cseg = d.seg;
+                const DevSeg sg = get_seg(a, d.seg);
+                const DevPiece cp = get_piece(a, sg.piece);
+                col_r = cp.r;
+                col_period = cp.period;
+            }
+            if (d.info & kColFirst) {
+                eval_window<C>(win, col_r, col_period, d.phase0, lane);
+                __syncwarp();
+            }
+            stream_tile_column<C, IN, OUT>(raw, out_s, win, d.info & 0xffu, lane);
+        } else {
+            const uint32_t k0 = d.k0;
+            if (k0 >= p.k_end || k0 < p.k_begin) {
+                pi = find_piece(a, k0 < p.k_begin ? 0 : pi, k0);
+                p = get_piece(a, pi);
+            }
+            const bool fast = k0 + d.nsamp <= p.k_end;
+            if (fast) {
+                if (lane == 0) issue_next(s);
+                refilled = true;
+                if (p.tab == kNoTab)
+                    stream_tile_direct<C, IN, OUT>(raw, out_s, p, k0, lane);
+                else if (pi == a.smem_piece)
+                    stream_tile<C, IN, OUT, kTabShared>(raw, out_s, p, k0, tab_s, plane_len, lane);
+                else
+                    stream_tile<C, IN, OUT, kTabGlobal>(raw, out_s, p, k0, a.tables + p.tab, 0, lane);
+            } else {
+                stream_tile_slow<C, IN, OUT>(a, pi, in_s, out_s, k0, d.nsamp, lane);
+                __syncwarp();
+            }
+        }
+        if (!refilled && lane == 0) issue_next(s);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(gout + (size_t)d.k0 * kOutBps, out_s, d.nsamp * kOutBps);
+            bulk_commit();
+        }
+    }
+    if (lane == 0) bulk_wait_all();
+
+    // sub-granule end of the buffer (fewer than kGran samples): pipeline 0 mixes it straight from
+    // global memory, sample by sample
+    if (a.tail_begin < a.nsamples && pipe == 0) {
+        pi = find_piece(a, 0, a.tail_begin);
+        p = get_piece(a, pi);
+        for (uint32_t k = a.tail_begin + lane; k < a.nsamples; k += 32) {
+            if (k >= p.k_end) {
+                pi = find_piece(a, pi, k);
+                p = get_piece(a, pi);
+            }
+            const float2 ph = phasor(p.r, piece_samplenum(p, k - p.k_begin));
+            store_sample<OUT>(a.out, k, cmul_unfused(load_sample<IN>(a.in, k), ph));
+        }
+    }
+}
+
+// The lean variant for launches that are ONE GRID segment of whole tiles (const mode, the BASELINE
+// metric): no segment table, no descriptors -- tile i of pipeline p is tile p + i * npipes.  About
+// 100 fewer issued instructions per tile than the segmented loop above, which is what keeps the
+// table-in-shared-memory path HBM-bound at 8 samples per lane per tile.  The ragged end (fewer samples
+// than a tile) is mixed from global memory by the pipeline next in line.
+template <int IN, int OUT, int WARPS, int S, int U>
+__global__ void __launch_bounds__(WARPS * 32, 1) mix_grid_kernel(const __grid_constant__ MixArgs a)
 {
     using C = StreamCfg<IN, OUT, WARPS, S, U>;
     constexpr int G = C::G;
@@ -678,7 +1009,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
     __syncthreads();
 
     const uint32_t pipe = blockIdx.x * WARPS + warp, npipes = gridDim.x * WARPS;
-    const uint32_t ntiles = a.ntiles;   // full tiles
+    const uint32_t ntiles = a.nunits;   // one GRID segment of whole tiles: unit = tile
     const uint32_t mine = pipe < ntiles ? (ntiles - pipe + npipes - 1) / npipes : 0;
     const unsigned char* gin = static_cast<const unsigned char*>(a.in);
     unsigned char* gout = static_cast<unsigned char*>(a.out);
@@ -730,7 +1061,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
         } else {
             if (lane == 0) bulk_wait_read<S - 1>();
             __syncwarp();
-            stream_tile_slow<C, IN, OUT>(a, pi, in_s, out_s, k0, lane);
+            stream_tile_slow<C, IN, OUT>(a, pi, in_s, out_s, k0, C::kTileSamples, lane);
             __syncwarp();
             if (lane == 0 && i + S < mine) issue_load(i + S);
         }

@@ -169,6 +169,20 @@ def plan_trace(samplenum, shifts_hz, block_samples, samplerate, count):
     return trace, sn.value, int(npieces)
 
 
+def plan_tiles_trace(intype, outtype, samplenum, shifts_hz, block_samples, samplerate, count, npipes=148 * 20):
+    """Host walk of one kernel launch's work decomposition (segment builder + the kernel's tile iterator).
+    Returns (samplenum assigned to every sample, times each sample is covered, tail_begin, stats dict)."""
+    sh = np.ascontiguousarray(shifts_hz, dtype=np.float32)
+    trace = np.zeros(count, dtype=np.uint32)
+    cover = np.zeros(count, dtype=np.uint32)
+    stats = np.zeros(4, dtype=np.uint64)
+    tb = _lib.load().doppler_b200_plan_tiles_trace(int(intype), int(outtype), int(samplenum), _ptr(sh), sh.size, int(block_samples),
+                                                   int(samplerate), int(count), int(npipes), _ptr(trace), _ptr(cover), _ptr(stats))
+    if tb < 0:
+        raise DopplerError(EINVAL, f"plan_tiles_trace failed ({tb})")
+    return trace, cover, int(tb), dict(zip(("segments", "column_segments", "units", "tiles"), (int(x) for x in stats)))
+
+
 def doppler_hz(range_rate_km_sec, frequency):
     """main.rs:163."""
     return float(_lib.load().doppler_b200_doppler_hz(float(range_rate_km_sec), int(frequency)))

@@ -185,6 +185,18 @@ size_t doppler_b200_tracker_doppler_table(doppler_b200_tracker* tr, double start
 long doppler_b200_plan_trace(uint32_t* samplenum, const float* shift_hz_per_block, size_t nblocks,
                              uint64_t block_samples, uint32_t samplerate, uint64_t count, uint32_t* trace);
 
+/* Test/introspection hook (host only, no device needed): the work decomposition of ONE kernel
+ * launch over `count` samples (count <= 2^30) for a per-block schedule -- the same segment builder
+ * and the same tile iterator the sm_100a kernel runs, walked on the host for `npipes` pipelines.
+ * For every tile the samplenum of each of its samples is written to trace[k] and cover[k] is
+ * incremented (both arrays `count` long, caller-zeroed), so a test can check that every sample
+ * below the returned tail start is covered exactly once with the reference's samplenum.
+ * stats (optional, 4 words): segments, COLUMN segments, work units, tiles.  Returns tail_begin
+ * (samples from there to count are mixed one by one from global memory) or -1 on bad arguments. */
+long doppler_b200_plan_tiles_trace(int intype, int outtype, uint32_t samplenum, const float* shift_hz_per_block,
+                                   size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint64_t count,
+                                   uint32_t npipes, uint32_t* trace, uint32_t* cover, uint64_t* stats);
+
 /* Device self-test hook: evaluates the kernel's phasor routine, (cos, sin) of
  * theta = (-2*PI) * (r * f32(n)) (dsp.rs:121-122), for n = n0 .. n0+count-1 into host arrays. */
 int doppler_b200_phasor_probe(doppler_b200_ctx* ctx, float r, uint32_t n0, size_t count, float* cos_out, float* sin_out);

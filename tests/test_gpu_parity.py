@@ -252,3 +252,52 @@ def test_direct_fast_rows_match_oracle(oracle, mixer, shift, fs, sn0, n):
         want, sn_ref = oracle.mix(buf, intype, outtype, shift, fs, samplenum=sn0)
         assert sn == sn_ref
         check(oracle, got, want, outtype)
+
+
+# Periods above the shared-memory table size with several whole periods in the launch: COLUMN segments
+# (phasors of a column evaluated once, parked in shared memory, reused over rows; mixer_kernels.cuh).
+COLUMN_CASES = [
+    (-9876.54, 1_024_000, 0, 2_500_003),            # P = 111 145 (odd): rows at every alignment shift
+    (7321.7, 1_024_000, 17, 1_300_001),             # P = 55 244, starts mid-period
+    (-3_912_345.25, 200_000_000, 0, 700_000),       # P = 26 787
+    (12_345.678, 1_024_000, 0, 1_000_000),
+    (-1234.5, 96_000, 3, 900_002),
+]
+
+
+@pytest.mark.parametrize("shift,fs,sn0,n", COLUMN_CASES)
+def test_column_segments_match_oracle(oracle, mixer, shift, fs, sn0, n):
+    from doppler_b200 import dsp
+    _, _, _, stats = dsp.plan_tiles_trace(F32, F32, sn0, [shift], n, fs, n)
+    assert stats["column_segments"] >= 1, stats   # the case must actually take the COLUMN path
+    ones = np.zeros(2 * n, dtype=np.float32)
+    ones[0::2] = 1.0
+    got, sn = mixer.mix(ones.view(np.uint8), F32, F32, shift, fs, samplenum=sn0)
+    want, sn_ref = oracle.mix(ones.view(np.uint8), F32, F32, shift, fs, samplenum=sn0)
+    assert sn == sn_ref
+    check(oracle, got, want, F32)
+    rng = np.random.default_rng(n)
+    for intype, outtype in TYPE_PAIRS:
+        buf = make_input(rng, n, intype)
+        got, sn = mixer.mix(buf, intype, outtype, shift, fs, samplenum=sn0)
+        want, sn_ref = oracle.mix(buf, intype, outtype, shift, fs, samplenum=sn0)
+        assert sn == sn_ref
+        check(oracle, got, want, outtype)
+
+
+def test_column_segments_in_a_track_schedule(oracle, mixer):
+    """Several long-period pieces in one launch (one shift per second at 1.024 Msps, as the replay driver
+    produces), all four type pairs."""
+    rng = np.random.default_rng(77)
+    fs = 1_024_000
+    per_sec = fs * 4 // BUFFER_SIZE   # i16 blocks per second
+    shifts = np.concatenate([np.repeat(np.float32(s), per_sec) for s in (-9876.54, -9871.02, 7321.7, 5000.0, -3211.11)])
+    for intype, outtype in TYPE_PAIRS:
+        nbytes = shifts.size * BUFFER_SIZE - BPS[intype] * 777
+        if intype == F32:
+            nbytes = shifts.size * BUFFER_SIZE // 2   # f32 blocks hold half as many samples: 2.5 s of stream
+        buf = make_input(rng, nbytes // BPS[intype], intype)
+        got, sn = mixer.mix_blocks(buf, intype, outtype, shifts, fs)
+        want, sn_ref = oracle.mix_blocks(buf, intype, outtype, shifts, fs)
+        assert sn == sn_ref
+        check(oracle, got, want, outtype)

@@ -112,3 +112,48 @@ def test_replay_schedule_matches_reference_clock(oracle, intype, fs):
         assert not panicked
         got = dsp.replay_schedule(table, -2500, fs, intype, nbytes)
         assert np.array_equal(used.view(np.uint32), got.view(np.uint32)), (nbytes, fs)
+
+
+# ---- work decomposition of one kernel launch (GRID / COLUMN segments, mixer_kernels.cuh) -------------
+TILE_CASES = [
+    # (shift, fs, start samplenum, samples): periods above the shared-memory table size become COLUMN segments
+    (-9876.54, 1_024_000, 0, 3_000_001),          # P = 111 145 (odd): every row has a different alignment shift
+    (7321.7, 1_024_000, 0, 1_024_003),            # P = 55 244
+    (-3_912_345.25, 200_000_000, 12_345, 500_000),  # P = 26 787, starts mid-period
+    (4_000_000.5, 200_000_000, 0, 400_000),       # P = 4.9 M > samples: linear piece only, GRID
+    (-15000.0, 256000, 7, 100_003),               # P = 256: table piece, GRID only
+    (5000.0, 1_024_000, 0, 300_000),              # P = 1024
+    (0.0, 48000, 0, 10_001), (1.0, 2_000_000_000, 2**32 - 1000, 50_000),
+]
+
+
+@pytest.mark.parametrize("intype,outtype", [(dsp.I16, dsp.I16), (dsp.I16, dsp.F32), (dsp.F32, dsp.I16), (dsp.F32, dsp.F32)])
+@pytest.mark.parametrize("shift,fs,start,count", TILE_CASES)
+def test_launch_tiles_cover_every_sample_once_with_the_reference_samplenum(oracle, intype, outtype, shift, fs, start, count):
+    """The segment builder and the kernel's own tile iterator, walked on the host: every sample below the
+    sub-granule tail is covered by exactly one tile, and the samplenum the tile arithmetic assigns (COLUMN:
+    window entry of the parked phasors; GRID: closed-form piece) is the reference recurrence's."""
+    want, _ = oracle.samplenum_trace(start, shift, fs, count)
+    for npipes in (148 * 20, 7):
+        trace, cover, tail, stats = dsp.plan_tiles_trace(intype, outtype, start, [shift], count, fs, count, npipes)
+        assert count - tail < 4
+        assert np.all(cover[:tail] == 1) and np.all(cover[tail:] == 0), stats
+        assert np.array_equal(trace[:tail], want[:tail]), stats
+
+
+def test_launch_tiles_track_schedule(oracle):
+    """A per-block schedule (track mode): several periodic pieces with long periods in one launch."""
+    fs, block = 1_024_000, 2048
+    shifts = np.concatenate([np.repeat(np.float32(-9876.54), 700), np.repeat(np.float32(7321.7), 400),
+                             np.repeat(np.float32(5000.0), 100), np.repeat(np.float32(-3211.11), 900)])
+    count = shifts.size * block - 333
+    want = np.empty(count, dtype=np.uint32)
+    sn, k = 0, 0
+    for s in (-9876.54, 7321.7, 5000.0, -3211.11):
+        n = min(int((shifts == np.float32(s)).sum()) * block, count - k)
+        want[k:k + n], sn = oracle.samplenum_trace(sn, float(np.float32(s)), fs, n)
+        k += n
+    for it, ot in [(dsp.I16, dsp.I16), (dsp.F32, dsp.F32)]:
+        trace, cover, tail, stats = dsp.plan_tiles_trace(it, ot, 0, shifts, block, fs, count)
+        assert stats["column_segments"] >= 2, stats
+        assert np.all(cover[:tail] == 1) and np.array_equal(trace[:tail], want[:tail])

@@ -69,7 +69,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", default=None, help="substring filter on the case label")
+    ap.add_argument("--only", default=None, help="comma-separated substring filters on the case label")
     args = ap.parse_args()
     mixer = doppler_b200.Mixer(0)
     stream = torch.cuda.Stream()
@@ -91,7 +91,7 @@ def main():
     cases.append(("cfg5 irregular 7321 Hz @ 1.024 Msps, 1 s", I16, I16, 7321.0, 1_024_000, 1_024_000))
     cases.append(("cfg2 f32->i16 10 Msps shift 100000, 64 s", F32, I16, 100000.0, 10_000_000, 640_000_000 if not args.quick else 64_000_000))
     if args.only:
-        cases = [c for c in cases if args.only in c[0]]
+        cases = [c for c in cases if any(f in c[0] for f in args.only.split(","))]
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     recs = []
     with open(args.out, "w") as f:

@@ -318,7 +318,7 @@ static void run_stream(uint64_t n, uint32_t period, float r, int tabmode /*0 sme
     snprintf(name, sizeof name, "stream %s->%s W%d S%d U%d %s P%u", tname(IN), tname(OUT), WARPS, S, U,
              tabmode == 0 ? "smemtab" : tabmode == 1 ? "l2tab" : "direct", period);
     if (!want(name)) return;
-    auto kern = dmix::mix_stream_kernel<IN, OUT, WARPS, S, U>;
+    auto kern = dmix::mix_grid_kernel<IN, OUT, WARPS, S, U>;
     const size_t smem = C::kFixedSmem + (tabmode == 0 ? C::table_bytes(period) : 0);
     if (smem > 227 * 1024) return;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -332,6 +332,13 @@ static void run_stream(uint64_t n, uint32_t period, float r, int tabmode /*0 sme
     a.nsamples = (uint32_t)n;
     a.npieces = 1;
     a.ntiles = (uint32_t)(n / C::kTileSamples);
+    a.nsegs = 1;
+    a.nunits = a.ntiles;
+    a.tail_begin = a.ntiles * C::kTileSamples;   // one GRID segment of whole tiles
+    a.inl_segs[0].unit_begin = 0;
+    a.inl_segs[0].unit_end = a.ntiles;
+    a.inl_segs[0].k_begin = 0;
+    a.inl_segs[0].k_end = a.tail_begin;
     a.smem_piece = tabmode == 0 ? 0 : dmix::kNoPiece;
     DevPiece d;
     memset(&d, 0, sizeof d);
