@@ -27,25 +27,25 @@
 #define SEGV 0
 #endif
 #if SEGV == 1
-#define SEG_I16I16 16, 2, 4
-#define SEG_I16F32 12, 2, 4
-#define SEG_F32I16 16, 3, 3
-#define SEG_F32F32 24, 2, 2
+#define SEG_I16I16 16, 2, 3
+#define SEG_I16F32 16, 3, 3
+#define SEG_F32I16 16, 2, 3
+#define SEG_F32F32 16, 2, 2
 #elif SEGV == 2
 #define SEG_I16I16 12, 2, 5
 #define SEG_I16F32 12, 3, 5
-#define SEG_F32I16 20, 2, 4
-#define SEG_F32F32 20, 3, 2
-#elif SEGV == 3
-#define SEG_I16I16 8, 2, 6
-#define SEG_I16F32 8, 3, 6
 #define SEG_F32I16 12, 2, 4
 #define SEG_F32F32 12, 2, 4
+#elif SEGV == 3
+#define SEG_I16I16 8, 2, 6
+#define SEG_I16F32 12, 2, 4
+#define SEG_F32I16 16, 2, 4
+#define SEG_F32F32 16, 2, 3
 #else
 #define SEG_I16I16 12, 2, 4
 #define SEG_I16F32 12, 3, 4
-#define SEG_F32I16 20, 2, 3
-#define SEG_F32F32 20, 2, 2
+#define SEG_F32I16 16, 2, 4
+#define SEG_F32F32 12, 2, 4
 #endif
 
 using dmix::DevPiece;
@@ -55,12 +55,14 @@ using dmix::MixArgs;
 namespace {
 
 constexpr uint64_t kLaunchMaxSamples = 1ull << 30;   // k fits 32 bits with room for base + offset
-constexpr uint32_t kColumnMaxRows = 16;              // COLUMN segments: rows sharing one phasor evaluation, at most
+constexpr uint32_t kColumnMaxRows = 64;              // COLUMN segments: rows sharing one phasor evaluation, at most
+constexpr uint32_t kUnitsPerPipe = 16;               // ... halved until the launch has this many work units per pipeline
 constexpr uint32_t kColumnMinRows = 2;               // fewer whole periods than this: evaluate per sample instead
 constexpr size_t kArenaMaxEntries = 64ull << 20;     // 512 MiB of (cos, sin) pairs
 constexpr uint32_t kSmemTabMaxEntries = 4096;        // 32 KiB of shared memory per CTA at most
 constexpr size_t kHostChunkBytes = 32ull << 20;      // host-path pipeline chunk (input side)
 constexpr int kSlots = 3;
+constexpr uint32_t kUnitCounters = 1024;             // segmented launches that may be in flight at once
 
 std::string g_create_error;
 
@@ -96,6 +98,8 @@ struct doppler_b200_ctx {
     cudaEvent_t tables_ready = nullptr;
     bool tables_event_valid = false;
     Slot slots[kSlots];
+    uint32_t* unit_counters = nullptr;   // ring of work-unit counters for the segmented kernel (one per launch in flight)
+    uint32_t counter_next = 0;
     std::string err;
     uint64_t launches = 0;
 };
@@ -244,45 +248,64 @@ uint32_t build_segments(const std::vector<DevPiece>& dev, uint32_t nsamp, uint32
             g.k_end = e;
             g.piece = piece;
             g.unit_begin = units;
-            units += (e - b + T - 1) / T;
+            units += ((e - b + T - 1) / T + dmix::kGridUnitTiles - 1) / dmix::kGridUnitTiles;
             g.unit_end = units;
             segs.push_back(g);
         };
         for (size_t i = 0; i < dev.size() && rcap >= kColumnMinRows; i++) {
             const DevPiece& d = dev[i];
             if (d.period <= kSmemTabMaxEntries || d.tab != dmix::kNoTab) continue;
-            const uint64_t P = d.period, k_end = std::min<uint64_t>(d.k_end, tail_begin);
-            uint64_t k0 = (uint64_t)d.k_begin + (P - d.base) % P;                  // first sample with phase 0
-            if ((k0 & gmask) < std::max<uint64_t>(d.k_begin, cursor)) k0 += P;      // row 0 starts inside the piece, aligned
-            if (k0 >= k_end) continue;
-            const uint64_t rows = (k_end - k0) / P;
-            if (rows < kColumnMinRows) continue;
-            const uint32_t a_begin = (uint32_t)k0 & gmask, a_end = (uint32_t)(k0 + rows * P) & gmask;
-            push_grid(cursor, a_begin, cursor_piece);
+            const int64_t P = d.period;
+            // the granule-aligned inside of the piece; its sub-granule edges stay with the GRID segments
+            const int64_t kb = ((int64_t)std::max(d.k_begin, cursor) + gran - 1) & ~(int64_t)(gran - 1);
+            const int64_t ke = (int64_t)(std::min(d.k_end, tail_begin) & gmask);
+            if (ke - kb < (int64_t)kColumnMinRows * P) continue;
+            const int64_t kph0 = (int64_t)d.k_begin + (P - d.base) % P;   // first sample of the piece with phase 0
+            int64_t jlo = (kb - kph0) / P;                                // row holding kb (floor division)
+            if ((kb - kph0) % P < 0) jlo--;
+            const int64_t k0 = kph0 + jlo * P;                            // <= kb, may be negative
+            const uint32_t rows = (uint32_t)((ke - k0 + P - 1) / P);
+            push_grid(cursor, (uint32_t)kb, cursor_piece);
             DevSeg c;
             memset(&c, 0, sizeof c);
-            c.k_begin = a_begin;
-            c.k_end = a_end;
+            c.k_begin = (uint32_t)kb;
+            c.k_end = (uint32_t)ke;
             c.piece = (uint32_t)i;
-            c.rows = (uint32_t)rows;
-            const uint32_t groups = ((uint32_t)rows + rcap - 1) / rcap;
-            c.rows_per_unit = ((uint32_t)rows + groups - 1) / groups;
+            c.rows = rows;
+            const uint32_t groups = (rows + rcap - 1) / rcap;
+            c.rows_per_unit = (rows + groups - 1) / groups;
             c.ncols = (uint32_t)((P + gran - 1 + T - 1) / T);
             magic_for(c.ncols, &c.ncols_magic, &c.ncols_shift);
-            c.k0 = (uint32_t)k0;
+            c.k0 = (uint32_t)(int32_t)k0;
             c.period = d.period;
+            c.r = d.r;
             c.unit_begin = units;
             units += ((c.rows + c.rows_per_unit - 1) / c.rows_per_unit) * c.ncols;
             c.unit_end = units;
             segs.push_back(c);
-            cursor = a_end;
+            cursor = (uint32_t)ke;
             cursor_piece = (uint32_t)i;
         }
         push_grid(cursor, tail_begin, cursor_piece);
-        // fewer rows per unit (more, shorter units) until every pipeline has work
-        if (units >= npipes || rcap <= kColumnMinRows) break;
+        // fewer rows per unit (more, shorter units) until the pipelines can balance: units are claimed
+        // dynamically, so the end-of-launch idle time is about one unit in kUnitsPerPipe
+        if (units >= kUnitsPerPipe * npipes || rcap <= kColumnMinRows) break;
     }
     return tail_begin;
+}
+
+// index[i] = segment containing work unit i << kSegIndexShift (the kernel's iterator jumps through it)
+std::vector<uint32_t> build_seg_index(const std::vector<DevSeg>& segs)
+{
+    const uint32_t nunits = segs.empty() ? 0 : segs.back().unit_end;
+    std::vector<uint32_t> index((nunits >> dmix::kSegIndexShift) + 1);
+    uint32_t sgi = 0;
+    for (size_t i = 0; i < index.size(); i++) {
+        const uint32_t u = (uint32_t)i << dmix::kSegIndexShift;
+        while (sgi + 1 < segs.size() && u >= segs[sgi].unit_end) sgi++;
+        index[i] = sgi;
+    }
+    return index;
 }
 
 // Launch-relative device pieces of stream pieces clipped to [l0, l1) (tables not resolved: tab = kNoTab).
@@ -327,10 +350,12 @@ long tiles_trace(const std::vector<DevPiece>& dev, uint32_t nsamp, uint32_t npip
     a.pieces = dev.data();
     a.nsegs = (uint32_t)segs.size();
     a.segs = segs.data();
+    const std::vector<uint32_t> index = build_seg_index(segs);
+    a.seg_index = index.data();
     for (size_t i = 0; i < segs.size() && i < (size_t)dmix::kInlineSegs; i++) a.inl_segs[i] = segs[i];
     a.nunits = segs.empty() ? 0 : segs.back().unit_end;
     a.tail_begin = tail_begin;
-    uint64_t ncol = 0, ntiles = 0;
+    uint64_t ncol = 0, ntiles = 0, col_tiles = 0, col_windows = 0, col_samples = 0;
     for (const DevSeg& g : segs) ncol += g.rows != 0;
     for (uint32_t pipe = 0; pipe < npipes; pipe++) {
         dmix::TileIter<C> it;
@@ -339,8 +364,14 @@ long tiles_trace(const std::vector<DevPiece>& dev, uint32_t nsamp, uint32_t npip
         size_t pi = 0;
         while (it.next(a, d)) {
             ntiles++;
+            if (d.info & dmix::kColFlag) {
+                col_tiles++;
+                col_samples += d.nsamp;
+                col_windows += (d.info & dmix::kColFirst) != 0;
+            }
             if (d.nsamp == 0 || d.nsamp > (uint32_t)C::kTileSamples || (d.k0 | d.nsamp) % C::kGran) return -2;
-            for (uint32_t x = 0; x < d.nsamp; x++) {
+            if (d.skip >= d.nsamp || d.skip % C::kGran) return -4;
+            for (uint32_t x = d.skip; x < d.nsamp; x++) {
                 const uint32_t k = d.k0 + x;
                 if (k >= nsamp) return -3;
                 uint32_t n;
@@ -369,6 +400,10 @@ long tiles_trace(const std::vector<DevPiece>& dev, uint32_t nsamp, uint32_t npip
         stats[1] = ncol;
         stats[2] = a.nunits;
         stats[3] = ntiles;
+        stats[4] = col_tiles;
+        stats[5] = col_windows;
+        stats[6] = col_samples;
+        stats[7] = (uint64_t)C::kTileSamples;
     }
     return (long)tail_begin;
 }
@@ -451,15 +486,26 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         if (segs.size() <= (size_t)dmix::kInlineSegs) {
             for (size_t i = 0; i < segs.size(); i++) a.inl_segs[i] = segs[i];
         } else {
-            CUDA_TRY(ctx, cudaMallocAsync(&d_segs, segs.size() * sizeof(DevSeg), s));
-            CUDA_TRY(ctx, cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(DevSeg), cudaMemcpyHostToDevice, s));
+            // segments + the coarse unit -> segment index in one allocation
+            const std::vector<uint32_t> index = build_seg_index(segs);
+            const size_t seg_bytes = segs.size() * sizeof(DevSeg);
+            CUDA_TRY(ctx, cudaMallocAsync(&d_segs, seg_bytes + index.size() * sizeof(uint32_t), s));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_segs, segs.data(), seg_bytes, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(d_segs) + seg_bytes, index.data(), index.size() * sizeof(uint32_t),
+                                          cudaMemcpyHostToDevice, s));
             a.segs = d_segs;
+            a.seg_index = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(d_segs) + seg_bytes);
         }
         // persistent: one CTA per SM, every warp an independent pipeline over interleaved work units
         if (grid_only) a.nunits = nsamp / shape.tile_samples;   // whole tiles; the lean loop mixes the ragged end itself
         const uint32_t want = (a.nunits + shape.warps - 1) / shape.warps;
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->sm_count, want));
         const size_t smem = shape.fixed_smem + (smem_piece != dmix::kNoPiece ? shape.table_bytes(dev[smem_piece].period) : 0);
+        if (!grid_only) {
+            // work units are claimed from a counter: one per launch in flight, zeroed in stream order
+            a.unit_counter = ctx->unit_counters + (ctx->counter_next++ % kUnitCounters);
+            CUDA_TRY(ctx, cudaMemsetAsync(a.unit_counter, 0, sizeof(uint32_t), s));
+        }
         shape.kern<<<grid, shape.warps * 32, smem, s>>>(a);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
@@ -630,6 +676,7 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&ctx->unit_counters, kUnitCounters * sizeof(uint32_t));
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->tables_ready, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e2 == cudaSuccess; i++)
         for (int o = 0; o < 2 && e2 == cudaSuccess; o++) {
@@ -662,6 +709,7 @@ void doppler_b200_destroy(doppler_b200_ctx* ctx)
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->unit_counters) cudaFree(ctx->unit_counters);
     if (ctx->tables_ready) cudaEventDestroy(ctx->tables_ready);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -63,36 +63,45 @@ static_assert(sizeof(DevPiece) == 48, "DevPiece layout");
 // A launch is cut into SEGMENTS of two kinds (all sample indices launch-relative; segment bounds
 // are multiples of the alignment granule, so every bulk copy is 16-byte aligned):
 //   GRID    contiguous tiles of kTileSamples, one work unit per tile; may contain any pieces.
-//   COLUMN  `rows` whole periods of ONE periodic piece whose table does not fit shared memory.
-//           Row j starts at a_j = align_down(k0 + j * period).  A work unit is one column tile c
-//           (phases c*T - s_j ... of every row) over `rows_per_unit` consecutive rows: the warp
-//           evaluates the column's phasors ONCE (direct, bit-exact sincosf), parks them in shared
-//           memory and reuses them for every row, so evaluation cost per sample drops by the
-//           number of rows.  s_j = (k0 + j*period) - a_j (0 .. granule-1) is the row's phase shift.
+//   COLUMN  the granule-aligned inside [k_begin, k_end) of ONE periodic piece whose table does not
+//           fit shared memory, seen as `rows` periods: row j holds phase 0 at k0 + j * period (k0
+//           is signed: the first row may start before the piece) and owns the samples
+//           [a_j, a_j+1) clipped to the segment, a_j = align_down(k0 + j * period).  A work unit is
+//           one column tile c (phases c*T - s_j ... of every row) over `rows_per_unit` consecutive
+//           rows: the warp evaluates the column's phasors ONCE (direct, bit-exact sincosf), parks
+//           them in shared memory and reuses them for every row, so evaluation cost per sample
+//           drops by the number of rows.  s_j = (k0 + j*period) - a_j (0 .. granule-1) is the
+//           row's phase shift.
 struct DevSeg {
     uint32_t unit_begin, unit_end;   // work units [unit_begin, unit_end)
     uint32_t k_begin, k_end;         // samples [k_begin, k_end)
     uint32_t piece;                  // GRID: piece containing k_begin; COLUMN: the periodic piece
-    uint32_t rows;                   // COLUMN: whole periods covered; 0 -> GRID
+    uint32_t rows;                   // COLUMN: periods touched (the first and last may be partial); 0 -> GRID
     uint32_t rows_per_unit;          // COLUMN: rows sharing one phasor evaluation
     uint32_t ncols;                  // COLUMN: column tiles per row
     uint32_t ncols_magic, ncols_shift;   // division by ncols (x < 2^31)
-    uint32_t k0;                     // COLUMN: sample holding phase 0 of row 0
+    uint32_t k0;                     // COLUMN: sample holding phase 0 of row 0 (int32: may be negative)
     uint32_t period;                 // COLUMN: copy of the piece's period
+    float r;                         // COLUMN: copy of the piece's ratio
+    uint32_t pad[3];
 };
-static_assert(sizeof(DevSeg) == 48, "DevSeg layout");
+static_assert(sizeof(DevSeg) == 64, "DevSeg layout");
+constexpr int kSegIndexShift = 6;   // MixArgs::seg_index has one entry per 64 work units
 
 constexpr int kInlineSegs = 3;
 
 // One tile of work, produced by lane 0's iterator when it issues the tile's bulk load and read
 // back by the whole warp when the tile reaches the compute stage.
 struct TileDesc {
-    uint32_t k0;       // first sample
-    uint32_t nsamp;    // samples (granule multiple, <= kTileSamples); 0 = end of this warp's work
+    uint32_t k0;       // sample at tile offset 0 (int32: a clipped first tile may start before the buffer)
+    uint32_t nsamp;    // tile offsets [skip, nsamp) are this tile's samples (granule multiples, nsamp <= kTileSamples);
+                       // 0 = end of this warp's work
     uint32_t seg;      // segment index
     uint32_t info;     // COLUMN: kColFlag | kColFirst (evaluate the phasor window) | row shift s_j
-    uint32_t phase0;   // COLUMN: phase of the column's first sample (c * kTileSamples)
-    uint32_t pad[3];
+    uint32_t phase0;   // COLUMN: phase of the column's first sample (c * kTileSamples); GRID: piece to search from
+    uint32_t period;   // COLUMN: the piece's period
+    float r;           // COLUMN: the piece's ratio
+    uint32_t skip;     // leading tile offsets that belong to a neighbouring piece (COLUMN, first row only)
 };
 static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
 constexpr uint32_t kColFlag = 0x80000000u, kColFirst = 0x40000000u;
@@ -103,6 +112,8 @@ struct MixArgs {
     void* out;
     const DevPiece* pieces;   // global copy when npieces > kInlinePieces
     const DevSeg* segs;       // global copy when nsegs > kInlineSegs
+    const uint32_t* seg_index;   // with segs: segment containing work unit (i << kSegIndexShift), one entry per 64 units
+    uint32_t* unit_counter;      // segmented kernel: next unclaimed work unit (zeroed before the launch)
     const float2* tables;     // phasor arena: entry = (cos, sin)
     uint32_t nsamples;
     uint32_t npieces;
@@ -766,57 +777,109 @@ __device__ __forceinline__ void stream_tile_column(const uint32_t (&raw)[C::U][4
     }
 }
 
-// Lane 0's work iterator: expands this pipeline's work units (pipe, pipe + npipes, ...) into tiles.
+// Lane 0's work iterator: expands work units into tiles.  On the device, units are claimed
+// kUnitChunk at a time from a global counter (a COLUMN unit costs 2-16 tiles plus a window evaluation,
+// a GRID unit kGridUnitTiles tiles: a static split left ~10 % of the SMs idle at the end of a track-mode launch);
+// the claim for the NEXT chunk is issued when a chunk starts, so its latency hides behind the
+// chunk's tiles.  On the host (doppler_b200_plan_tiles_trace) pipeline p walks chunks p, p + npipes, ...
+constexpr uint32_t kUnitChunk = 1;
+constexpr uint32_t kGridUnitTiles = 8;   // a GRID work unit is this many consecutive tiles (comparable to a COLUMN unit)
+
 template <typename C>
 struct TileIter {
-    uint32_t u, step, nunits;
+    uint32_t u, uend, next_base, step, nunits;
     uint32_t seg;
     DevSeg sg;
     uint32_t c, j, jend;
-    bool first, started;
+    bool first;
+
+    __host__ __device__ __forceinline__ uint32_t claim(const MixArgs& a)
+    {
+#if defined(__CUDA_ARCH__)
+        return atomicAdd(a.unit_counter, kUnitChunk);
+#else
+        (void)a;
+        const uint32_t b = next_base + step;   // host walk: static striding over chunks
+        return b;
+#endif
+    }
 
     __host__ __device__ __forceinline__ void init(const MixArgs& a, uint32_t pipe, uint32_t npipes)
     {
-        u = pipe;
-        step = npipes;
+        step = npipes * kUnitChunk;
         nunits = a.nunits;
+        u = uend = 0;
+#if defined(__CUDA_ARCH__)
+        (void)pipe;
+        next_base = claim(a);
+#else
+        next_base = pipe * kUnitChunk;
+#endif
         seg = 0;
         sg = get_seg(a, 0);
         c = j = jend = 0;
-        first = started = false;
+        first = false;
     }
 
     __host__ __device__ __forceinline__ bool next(const MixArgs& a, TileDesc& d)
     {
         constexpr uint32_t T = C::kTileSamples, GM = ~(uint32_t)(C::kGran - 1);
         for (;;) {
-            if (j < jend) {   // rows left in the current column unit
-                const uint32_t kj = sg.k0 + j * sg.period;
-                const uint32_t aj = kj & GM, aj1 = (kj + sg.period) & GM;
-                const uint32_t start = aj + c * T;
+            if (j < jend && sg.rows == 0) {   // tiles left in the current GRID unit
+                const uint32_t start = sg.k_begin + j * T;
                 j++;
-                if (start >= aj1) continue;   // this row is a few samples shorter than the last column
-                d.k0 = start;
-                d.nsamp = aj1 - start < T ? aj1 - start : T;
-                d.seg = seg;
-                d.info = kColFlag | (first ? kColFirst : 0u) | (kj - aj);
-                d.phase0 = c * T;
-                first = false;
-                return true;
-            }
-            if (started) u += step;
-            started = true;
-            if (u >= nunits) return false;
-            while (u >= sg.unit_end) sg = get_seg(a, ++seg);
-            const uint32_t v = u - sg.unit_begin;
-            if (sg.rows == 0) {
-                const uint32_t start = sg.k_begin + v * T;
                 d.k0 = start;
                 d.nsamp = sg.k_end - start < T ? sg.k_end - start : T;
                 d.seg = seg;
                 d.info = 0;
-                d.phase0 = 0;
+                d.phase0 = sg.piece;
+                d.period = 0;
+                d.r = 0.0f;
+                d.skip = 0;
                 return true;
+            }
+            if (j < jend) {   // rows left in the current COLUMN unit
+                const int32_t kj = (int32_t)sg.k0 + (int32_t)(j * sg.period);
+                const int32_t aj = kj & (int32_t)GM, aj1 = (kj + (int32_t)sg.period) & (int32_t)GM;
+                const int32_t start = aj + (int32_t)(c * T);
+                j++;
+                int32_t hi = start + (int32_t)T < aj1 ? start + (int32_t)T : aj1;   // the row's last column is short
+                if (hi > (int32_t)sg.k_end) hi = (int32_t)sg.k_end;                   // the segment's last row is partial
+                const int32_t lo = start > (int32_t)sg.k_begin ? start : (int32_t)sg.k_begin;   // so is its first
+                if (lo >= hi) continue;
+                d.k0 = (uint32_t)start;
+                d.skip = (uint32_t)(lo - start);
+                d.nsamp = (uint32_t)(hi - start);
+                d.seg = seg;
+                d.info = kColFlag | (first ? kColFirst : 0u) | (uint32_t)(kj - aj);
+                d.phase0 = c * T;
+                d.period = sg.period;
+                d.r = sg.r;
+                first = false;
+                return true;
+            }
+            if (u >= uend) {   // chunk exhausted: take the one claimed earlier, claim the one after
+                if (next_base >= nunits) return false;
+                u = next_base;
+                uend = u + kUnitChunk < nunits ? u + kUnitChunk : nunits;
+                next_base = claim(a);
+            }
+            if (u >= sg.unit_end) {
+                // jump through the coarse unit -> segment index, then walk the last few segments
+                if (a.nsegs > (uint32_t)kInlineSegs) {
+                    const uint32_t hint = a.seg_index[u >> kSegIndexShift];
+                    if (hint > seg) seg = hint - 1;
+                }
+                do sg = get_seg(a, ++seg);
+                while (u >= sg.unit_end);
+            }
+            const uint32_t v = u - sg.unit_begin;
+            u++;
+            if (sg.rows == 0) {
+                const uint32_t ntiles = (sg.k_end - sg.k_begin + T - 1) / T;
+                j = v * kGridUnitTiles;
+                jend = j + kGridUnitTiles < ntiles ? j + kGridUnitTiles : ntiles;
+                continue;
             }
             const uint32_t g = (uint32_t)(((uint64_t)v * sg.ncols_magic) >> sg.ncols_shift);
             c = v - g * sg.ncols;
@@ -868,15 +931,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
 
     // lane 0: iterator + load issue; the descriptor travels to the compute stage through shared memory
     TileIter<C> it;
-    it.init(a, pipe, npipes);
+    if (lane == 0) it.init(a, pipe, npipes);   // lane 0 only: init claims a chunk of work units
     auto issue_next = [&](uint32_t s) {   // lane 0 only
         TileDesc d;
         if (it.next(a, d)) {
-            const uint32_t bytes = d.nsamp * kInBps;
+            const uint32_t bytes = (d.nsamp - d.skip) * kInBps;
             mbar_expect_tx(&full[s], bytes);
-            bulk_g2s(ring_in + s * C::kTileIn, gin + (size_t)d.k0 * kInBps, bytes, &full[s]);
+            bulk_g2s(ring_in + s * C::kTileIn + d.skip * kInBps, gin + (size_t)(d.k0 + d.skip) * kInBps, bytes, &full[s]);
         } else {
-            d.k0 = d.nsamp = d.seg = d.info = d.phase0 = 0;
+            d.k0 = d.nsamp = d.seg = d.info = d.phase0 = d.period = d.skip = 0;
+            d.r = 0.0f;
         }
         desc_ring[s] = d;
     };
@@ -885,9 +949,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
 
     uint32_t pi = 0;                 // GRID: cached piece
     DevPiece p = get_piece(a, 0);
-    uint32_t cseg = 0xffffffffu;     // COLUMN: cached segment -> its piece's r / period
-    float col_r = 0.0f;
-    uint32_t col_period = 1;
     for (uint32_t i = 0;; i++) {
         const uint32_t s = i % S;
         __syncwarp();
@@ -914,22 +975,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
         if (d.info & kColFlag) {
             if (lane == 0) issue_next(s);
             refilled = true;
-            if (d.seg != cseg) {
-                cseg = d.seg;
-                const DevSeg sg = get_seg(a, d.seg);
-                const DevPiece cp = get_piece(a, sg.piece);
-                col_r = cp.r;
-                col_period = cp.period;
-            }
             if (d.info & kColFirst) {
-                eval_window<C>(win, col_r, col_period, d.phase0, lane);
+                eval_window<C>(win, d.r, d.period, d.phase0, lane);
                 __syncwarp();
             }
             stream_tile_column<C, IN, OUT>(raw, out_s, win, d.info & 0xffu, lane);
         } else {
             const uint32_t k0 = d.k0;
             if (k0 >= p.k_end || k0 < p.k_begin) {
-                pi = find_piece(a, k0 < p.k_begin ? 0 : pi, k0);
+                // the segment names the piece holding its first sample: walk forward from there (GRID
+                // segments between COLUMN segments hold a handful of pieces)
+                pi = max(d.phase0, k0 >= p.k_end ? pi : 0u);
+                while (k0 >= piece_end(a, pi)) pi++;
                 p = get_piece(a, pi);
             }
             const bool fast = k0 + d.nsamp <= p.k_end;
@@ -951,7 +1008,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-            bulk_s2g(gout + (size_t)d.k0 * kOutBps, out_s, d.nsamp * kOutBps);
+            bulk_s2g(gout + (size_t)(d.k0 + d.skip) * kOutBps, out_s + d.skip * kOutBps, (d.nsamp - d.skip) * kOutBps);
             bulk_commit();
         }
     }

@@ -4,6 +4,9 @@
 
 #include <math.h>
 #include <string.h>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 
 #ifdef __FAST_MATH__
 #error "plan.cpp must not be built with -ffast-math"
@@ -36,22 +39,92 @@ static inline bool hit(float r, uint32_t n)
 
 bool reset_test(float r, uint32_t n) { return hit(r, n); }
 
-#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
-__attribute__((target_clones("avx512f", "avx2", "default")))
+// Scalar scan (any ISA; also the tail / wrap-around path of the vector scans).
+static uint64_t first_hit_scalar(float r, uint32_t n0, uint64_t limit)
+{
+    for (uint64_t i = 0; i < limit; i++)
+        if (hit(r, n0 + (uint32_t)i)) return i;
+    return limit;
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+// The same test on 8 / 16 consecutive n per step.  The planner runs this scan once per change of
+// shift (track mode: once per second of stream) over up to one period; the auto-vectoriser does
+// not vectorise hit() (u32 -> f32 conversion), which left the host planning of a 600-run schedule
+// 10x slower than the kernels that mix it.  n < 2^31 here, so the signed conversion is exact.
+__attribute__((target("avx2"))) static uint64_t first_hit_avx2(float r, uint32_t n0, uint64_t limit)
+{
+    const __m256 vr = _mm256_set1_ps(r), two23 = _mm256_set1_ps(8388608.0f), fmax = _mm256_set1_ps(3.40282347e+38f);
+    const __m256 absmask = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff));
+    __m256i vn = _mm256_add_epi32(_mm256_set1_epi32((int)n0), _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7));
+    const __m256i step = _mm256_set1_epi32(8);
+    uint64_t i = 0;
+    for (; i + 8 <= limit; i += 8, vn = _mm256_add_epi32(vn, step)) {
+        const __m256 x = _mm256_mul_ps(vr, _mm256_cvtepi32_ps(vn));
+        const __m256 ax = _mm256_and_ps(x, absmask);
+        const __m256 small = _mm256_cmp_ps(ax, two23, _CMP_LT_OQ);
+        const __m256 back = _mm256_cvtepi32_ps(_mm256_cvttps_epi32(_mm256_and_ps(x, small)));
+        const __m256 small_int = _mm256_and_ps(small, _mm256_cmp_ps(back, x, _CMP_EQ_OQ));
+        const __m256 big = _mm256_and_ps(_mm256_cmp_ps(ax, two23, _CMP_GE_OQ), _mm256_cmp_ps(ax, fmax, _CMP_LE_OQ));
+        const int m = _mm256_movemask_ps(_mm256_or_ps(small_int, big));
+        if (m) return i + (uint64_t)__builtin_ctz((unsigned)m);
+    }
+    const uint64_t d = first_hit_scalar(r, n0 + (uint32_t)i, limit - i);
+    return i + d;
+}
+
+__attribute__((target("avx512f"))) static uint64_t first_hit_avx512(float r, uint32_t n0, uint64_t limit)
+{
+    const __m512 vr = _mm512_set1_ps(r), two23 = _mm512_set1_ps(8388608.0f), fmax = _mm512_set1_ps(3.40282347e+38f);
+    __m512i vn = _mm512_add_epi32(_mm512_set1_epi32((int)n0), _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15));
+    const __m512i step = _mm512_set1_epi32(16);
+    uint64_t i = 0;
+    for (; i + 16 <= limit; i += 16, vn = _mm512_add_epi32(vn, step)) {
+        const __m512 x = _mm512_mul_ps(vr, _mm512_cvtepi32_ps(vn));
+        const __m512 ax = _mm512_abs_ps(x);
+        const __mmask16 small = _mm512_cmp_ps_mask(ax, two23, _CMP_LT_OQ);
+        const __m512 xs = _mm512_maskz_mov_ps(small, x);
+        const __m512 back = _mm512_cvtepi32_ps(_mm512_cvttps_epi32(xs));
+        const __mmask16 small_int = _mm512_mask_cmp_ps_mask(small, back, x, _CMP_EQ_OQ);
+        const __mmask16 big = _mm512_mask_cmp_ps_mask(_mm512_cmp_ps_mask(ax, two23, _CMP_GE_OQ), ax, fmax, _CMP_LE_OQ);
+        const unsigned m = (unsigned)(small_int | big);
+        if (m) return i + (uint64_t)__builtin_ctz(m);
+    }
+    const uint64_t d = first_hit_scalar(r, n0 + (uint32_t)i, limit - i);
+    return i + d;
+}
 #endif
+
 uint64_t first_hit(float r, uint32_t n0, uint64_t limit)
 {
-    constexpr uint64_t kChunk = 4096;
-    for (uint64_t done = 0; done < limit; done += kChunk) {
-        const uint64_t m = limit - done < kChunk ? limit - done : kChunk;
+    uint64_t done = 0;
+#if defined(__x86_64__) && defined(__GNUC__)
+    static const int isa = __builtin_cpu_supports("avx512f") ? 2 : __builtin_cpu_supports("avx2") ? 1 : 0;
+    // vector scans need n < 2^31 throughout (signed conversion); the stretch beyond is scalar
+    while (isa && done < limit) {
         const uint32_t nb = n0 + (uint32_t)done;
-        unsigned any = 0;
-        for (uint64_t i = 0; i < m; i++) any |= (unsigned)hit(r, nb + (uint32_t)i);
-        if (any) {
-            for (uint64_t i = 0; i < m; i++)
-                if (hit(r, nb + (uint32_t)i)) return done + i;
-        }
+        if (nb >= 0x80000000u) break;
+        const uint64_t room = 0x80000000ull - nb, span = limit - done < room ? limit - done : room;
+        const uint64_t d = isa == 2 ? first_hit_avx512(r, nb, span) : first_hit_avx2(r, nb, span);
+        if (d < span) return done + d;
+        done += span;
+        if (span == room) break;   // continue scalar through the sign boundary and beyond
     }
+#endif
+    // scalar: no vector ISA, or n >= 2^31 (including the u32 wrap-around)
+    while (done < limit) {
+        const uint32_t nb = n0 + (uint32_t)done;
+        uint64_t span = limit - done;
+#if defined(__x86_64__) && defined(__GNUC__)
+        if (isa && nb < 0x80000000u) break;   // wrapped back below 2^31: hand back to the vector scan
+#endif
+        const uint64_t room = 0x100000000ull - nb;   // up to the u32 wrap
+        if (span > room) span = room;
+        const uint64_t d = first_hit_scalar(r, nb, span);
+        if (d < span) return done + d;
+        done += span;
+    }
+    if (done < limit) return done + first_hit(r, n0 + (uint32_t)done, limit - done);
     return limit;
 }
 
@@ -94,7 +167,19 @@ uint64_t Planner::hit_distance(float r, uint32_t n, uint64_t count)
         }
         if (!pi.period && (uint64_t)n + count - 1 <= pi.searched) return count;
     }
-    return first_hit(r, n, count);
+    // Arbitrary start state (a shift change in track mode lands anywhere): scan, and remember the
+    // answer -- a caller that replays or re-plans the same schedule pays for each scan once.
+    const uint64_t key = ((uint64_t)fbits(r) << 32) | n;
+    auto it = hits_.find(key);
+    if (it != hits_.end()) {
+        if (it->second.found) return it->second.dist < count ? it->second.dist : count;
+        if (it->second.dist >= count) return count;   // dist = samples known to be hit-free
+    }
+    if (hits_.size() > (1u << 16)) hits_.clear();
+    const uint64_t done = it != hits_.end() ? it->second.dist : 0;
+    const uint64_t d = done + first_hit(r, n + (uint32_t)done, count - done);
+    hits_[key] = HitInfo{d < count ? d : count, d < count};
+    return d < count ? d : count;
 }
 
 void Planner::plan(const std::vector<Run>& runs, uint64_t k0, uint32_t* samplenum, std::vector<Piece>* out)
@@ -144,14 +229,25 @@ std::vector<Run> runs_from_blocks(const float* shift_hz, size_t nblocks, uint64_
 {
     std::vector<Run> runs;
     uint64_t left = total_samples;
-    for (size_t b = 0; b < nblocks && left > 0; b++) {
-        const uint64_t c = left < block_samples ? left : block_samples;
+    // Replay schedules repeat one shift for a whole second of blocks (millions of blocks at 200 Msps):
+    // find the end of each stretch of identical shift bits by galloping with memcmp (the array against
+    // itself one element on), then form the ratio once per stretch.
+    const size_t need = (size_t)((total_samples + block_samples - 1) / block_samples);
+    const size_t nb = need < nblocks ? need : nblocks;
+    constexpr size_t kGallop = 1024;
+    for (size_t b = 0; b < nb && left > 0;) {
+        size_t e = b + 1;
+        while (e + kGallop <= nb && memcmp(shift_hz + e - 1, shift_hz + e, kGallop * sizeof(float)) == 0) e += kGallop;
+        while (e < nb && fbits(shift_hz[e]) == fbits(shift_hz[b])) e++;
+        const uint64_t span = (uint64_t)(e - b) * block_samples;
+        const uint64_t c = left < span ? left : span;
         const float r = ratio(shift_hz[b], samplerate);
         if (!runs.empty() && fbits(runs.back().r) == fbits(r))
             runs.back().count += c;
         else
             runs.push_back(Run{c, r});
         left -= c;
+        b = e;
     }
     return runs;
 }

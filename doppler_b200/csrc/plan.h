@@ -66,7 +66,12 @@ private:
         uint64_t searched = 0;   // n in [1, searched] are known not to hit (when period == 0)
         uint64_t period = 0;
     };
+    struct HitInfo {
+        uint64_t dist;   // found: samples until the first hit; otherwise: samples known to be hit-free
+        bool found;
+    };
     std::unordered_map<uint32_t, PeriodInfo> cache_;   // key: bit pattern of r
+    std::unordered_map<uint64_t, HitInfo> hits_;       // key: (bits of r, start samplenum) -> first_hit result
     const PeriodInfo& learn(float r, uint32_t n, uint64_t count);
     uint64_t hit_distance(float r, uint32_t n, uint64_t count);
 };

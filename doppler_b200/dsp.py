@@ -175,12 +175,13 @@ def plan_tiles_trace(intype, outtype, samplenum, shifts_hz, block_samples, sampl
     sh = np.ascontiguousarray(shifts_hz, dtype=np.float32)
     trace = np.zeros(count, dtype=np.uint32)
     cover = np.zeros(count, dtype=np.uint32)
-    stats = np.zeros(4, dtype=np.uint64)
+    stats = np.zeros(8, dtype=np.uint64)
     tb = _lib.load().doppler_b200_plan_tiles_trace(int(intype), int(outtype), int(samplenum), _ptr(sh), sh.size, int(block_samples),
                                                    int(samplerate), int(count), int(npipes), _ptr(trace), _ptr(cover), _ptr(stats))
     if tb < 0:
         raise DopplerError(EINVAL, f"plan_tiles_trace failed ({tb})")
-    return trace, cover, int(tb), dict(zip(("segments", "column_segments", "units", "tiles"), (int(x) for x in stats)))
+    return trace, cover, int(tb), dict(zip(("segments", "column_segments", "units", "tiles", "column_tiles", "windows", "column_samples", "tile_samples"),
+                                         (int(x) for x in stats)))
 
 
 def doppler_hz(range_rate_km_sec, frequency):

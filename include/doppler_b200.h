@@ -191,7 +191,8 @@ long doppler_b200_plan_trace(uint32_t* samplenum, const float* shift_hz_per_bloc
  * For every tile the samplenum of each of its samples is written to trace[k] and cover[k] is
  * incremented (both arrays `count` long, caller-zeroed), so a test can check that every sample
  * below the returned tail start is covered exactly once with the reference's samplenum.
- * stats (optional, 4 words): segments, COLUMN segments, work units, tiles.  Returns tail_begin
+ * stats (optional, 8 words): segments, COLUMN segments, work units, tiles, COLUMN tiles, phasor windows
+ * evaluated, samples in COLUMN tiles, samples per full tile.  Returns tail_begin
  * (samples from there to count are mixed one by one from global memory) or -1 on bad arguments. */
 long doppler_b200_plan_tiles_trace(int intype, int outtype, uint32_t samplenum, const float* shift_hz_per_block,
                                    size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint64_t count,

@@ -64,6 +64,61 @@ def run_case(mixer, stream, flush, label, intype, outtype, shift, fs, n, iters):
     return rec
 
 
+def overpass_shifts(fs, secs, ftx, tc, offset, intype, nsamples):
+    """Per-block shift schedule of the reference's replay driver for an analytic overpass."""
+    import numpy as np
+    from doppler_b200 import dsp
+    t = np.arange(secs + 2, dtype=np.float64)
+    v, d = 7500.0, 700e3
+    rr_km_s = v * v * (t - tc) / np.sqrt(d * d + (v * (t - tc)) ** 2) / 1000.0
+    table = np.array([dsp.doppler_hz(x, ftx) for x in rr_km_s])
+    return dsp.replay_schedule(table, offset, fs, intype, nsamples * BPS[intype])
+
+
+def run_track_case(mixer, stream, label, intype, outtype, fs, shifts, n, seed, iters):
+    dev = torch.device("cuda", 0)
+    x = torch.empty(n * BPS[intype], dtype=torch.uint8, device=dev)
+    if intype == F32:
+        x.view(torch.float32).uniform_(-0.7, 0.7)
+    else:
+        v = x.view(torch.int16)
+        for k in range(0, v.numel(), 1 << 28):
+            v[k:k + (1 << 28)].copy_(torch.randint(-20000, 20000, (min(1 << 28, v.numel() - k),), device=dev, dtype=torch.int16))
+    y = torch.empty(n * BPS[outtype], dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    # the host plans every call (runs, pieces, segments) before it launches: time `iters` calls queued back to
+    # back, so the planning of call i+1 overlaps the kernels of call i as it does for a streaming caller, and
+    # one call alone (planning + kernels, nothing to overlap with)
+    import time
+    times, single = [], []
+    with torch.cuda.stream(stream):
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(iters):
+                mixer.mix_blocks_dev(x.data_ptr(), x.numel(), intype, outtype, shifts, fs, seed, y.data_ptr(), y.numel(), stream=stream.cuda_stream)
+            e1.record(stream)
+            stream.synchronize()
+            if rep >= 1:
+                times.append(e0.elapsed_time(e1) * 1e-3 / iters)
+        for rep in range(3):
+            t0 = time.perf_counter()
+            mixer.mix_blocks_dev(x.data_ptr(), x.numel(), intype, outtype, shifts, fs, seed, y.data_ptr(), y.numel(), stream=stream.cuda_stream)
+            t1 = time.perf_counter()
+            stream.synchronize()
+            single.append((t1 - t0, time.perf_counter() - t0))
+    med, best = statistics.median(times), min(times)
+    bps = BPS[intype] + BPS[outtype]
+    rec = {"case": label, "in": NAME[intype], "out": NAME[outtype], "shift_hz": "schedule", "samplerate": fs, "samples": n,
+           "median_us": med * 1e6, "best_us": best * 1e6, "msps_median": n / med / 1e6, "msps_best": n / best / 1e6,
+           "gbs_median": n * bps / med / 1e9, "frac_of_measured_peak": n * bps / med / 1e9 / peak(), "l2_flushed": False,
+           "iters": iters, "host_plan_ms": min(a for a, _ in single) * 1e3, "single_call_ms": min(b for _, b in single) * 1e3,
+           "note": "median over 3 batches of `iters` calls queued back to back (CUDA events around the batch)"}
+    del x, y
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
@@ -97,6 +152,26 @@ def main():
     with open(args.out, "w") as f:
         for c in cases:
             rec = run_case(mixer, stream, flush, *c, args.iters)
+            recs.append(rec)
+            f.write(json.dumps(rec) + "\n")
+            f.flush()
+            print(f"{rec['case']:55s} {rec['msps_median']:12.1f} Msps  {rec['gbs_median']:8.1f} GB/s  {rec['frac_of_measured_peak']:.3f}")
+        # (c) track mode at full size: cfg3 (600 s @ 1.024 Msps i16) and one GPU's slice of cfg4 (f32 @ 200 Msps)
+        track = []
+        if not args.quick:
+            from doppler_b200 import slicing
+            n3 = 600 * 1_024_000
+            track.append(("cfg3 track replay 600 s @ 1.024 Msps i16->i16", I16, I16, 1_024_000,
+                          overpass_shifts(1_024_000, 600, 437_505_000, 300.0, 5000, I16, n3), n3, 0))
+            total = 60 * 200_000_000
+            b, e = slicing.slice_bounds(total, 8, 3, F32)
+            sh = overpass_shifts(200_000_000, 60, 4_200_000_000, 30.0, 0, F32, total)
+            track.append(("cfg4 track f32->f32 @ 200 Msps, slice 3 of 8 (1.5 G samples)", F32, F32, 200_000_000,
+                          sh[b // slicing.block_samples(F32):], e - b, slicing.seed_blocks(sh, F32, 200_000_000, b)))
+        for c in track:
+            if args.only and not any(f in c[0] for f in args.only.split(",")):
+                continue
+            rec = run_track_case(mixer, stream, *c, max(3, args.iters // 4))
             recs.append(rec)
             f.write(json.dumps(rec) + "\n")
             f.flush()
