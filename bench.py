@@ -101,7 +101,8 @@ class ClockSampler:
                 except Exception:
                     pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed region + 0.7 s of the same steps (the timed region alone is shorter than the sampling period)"}
 
 
 def measured_peak_gbs():
@@ -232,9 +233,17 @@ def main():
         step()
     ev1.record(tstream)
     barrier()
-    t1 = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = mixer.launch_count - l0
+    # The timed region lasts ~K ms, shorter than nvidia-smi's sampling period: keep the SAME steps running
+    # (untimed) for a moment so that the clock / throttle record is taken under this workload's load.
+    if rank == 0:
+        t_hold = time.time() + 0.7
+        while time.time() < t_hold:
+            for _ in range(20):
+                step()
+            torch.cuda.synchronize()
+    t1 = time.time()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -250,7 +259,7 @@ def main():
     # one mixer launch per step on this rank (the phasor table is built once, in warm-up)
     achieved = BYTES_PER_SAMPLE * n / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "dmix::mix_stream_kernel<F32,I16,...> (per-warp cp.async.bulk pipelines)", "bytes_per_sample": BYTES_PER_SAMPLE,
+                "peak_source": peak_src, "kernel": "dmix::mix_grid_kernel<F32,I16,16,2,3> (per-warp cp.async.bulk pipelines, phasor table in shared memory)", "bytes_per_sample": BYTES_PER_SAMPLE,
                 "note": "per-GPU; time = CUDA events on the launch stream over the timed region / launches"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
