@@ -105,6 +105,29 @@ class ClockSampler:
                 "window": "timed region + 0.7 s of the same steps (the timed region alone is shorter than the sampling period)"}
 
 
+def bind_near_gpu(local):
+    """Pin this process to the CPUs NVML reports as local to its GPU (same NUMA node / PCIe root), so that the
+    pinned host buffers of the e2e leg are first-touched next to the GPU.  With 8 ranks pulling ~50 GB/s each
+    from host memory, buffers on the far socket halve the end-to-end rate.  Returns the previous affinity
+    (to restore for the CPU baseline) or None when NVML / the cpuset does not allow it."""
+    try:
+        import pynvml
+        import torch
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1} & prev
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -278,6 +301,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         import ctypes
+        prev_affinity = bind_near_gpu(local)
         from doppler_b200 import _lib
         lib = _lib.load()
         ne = min(n, 16 * FS)  # 160 Msamples per step: 1.28 GB in, 0.64 GB out through PCIe
@@ -313,9 +337,12 @@ def main():
             te = float(t.item())
         e2e = {"value": world * ne * ke / te / 1e6, "unit": UNIT, "h2d_bytes_per_step": 8 * ne, "d2h_bytes_per_step": 4 * ne,
                "samples_per_gpu_per_step": ne, "steps": ke,
-               "api": "doppler_b200_mix (host buffers, pinned via doppler_b200_host_alloc; 32 MiB chunks, 3-slot H2D/kernel/D2H pipeline)"}
+               "api": "doppler_b200_mix (host buffers, pinned via doppler_b200_host_alloc; 32 MiB chunks, 3-slot H2D/kernel/D2H pipeline)",
+               "cpu_affinity": "GPU-local CPUs (NVML)" if prev_affinity is not None else "unchanged"}
         lib.doppler_b200_host_free(hin)
         lib.doppler_b200_host_free(hout)
+        if prev_affinity is not None:
+            os.sched_setaffinity(0, prev_affinity)
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -62,13 +62,21 @@ constexpr size_t kArenaMaxEntries = 64ull << 20;     // 512 MiB of (cos, sin) pa
 constexpr uint32_t kSmemTabMaxEntries = 4096;        // 32 KiB of shared memory per CTA at most
 constexpr size_t kHostChunkBytes = 32ull << 20;      // host-path pipeline chunk (input side)
 constexpr int kSlots = 3;
-constexpr uint32_t kUnitCounters = 1024;             // segmented launches that may be in flight at once
+constexpr int kMetaSlots = 8;                        // pinned staging slots for launch metadata
 
 std::string g_create_error;
 
 struct TableRef {
     uint32_t off;
     uint32_t period;
+};
+
+struct MetaSlot {
+    void* host = nullptr;   // pinned staging image
+    void* dev = nullptr;    // its device copy (persistent: stream-ordered pool memory is trimmed at every synchronize)
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool used = false;
 };
 
 struct Slot {
@@ -98,8 +106,8 @@ struct doppler_b200_ctx {
     cudaEvent_t tables_ready = nullptr;
     bool tables_event_valid = false;
     Slot slots[kSlots];
-    uint32_t* unit_counters = nullptr;   // ring of work-unit counters for the segmented kernel (one per launch in flight)
-    uint32_t counter_next = 0;
+    MetaSlot meta[kMetaSlots];   // pinned staging for launch metadata (pieces, segments, work-unit counter)
+    uint32_t meta_next = 0;
     std::string err;
     uint64_t launches = 0;
 };
@@ -474,43 +482,61 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         a.nunits = segs.empty() ? 0 : segs.back().unit_end;
         a.tail_begin = tail_begin;
         a.smem_piece = smem_piece;
-        DevPiece* d_pieces = nullptr;
-        DevSeg* d_segs = nullptr;
-        if (dev.size() <= (size_t)dmix::kInlinePieces) {
-            for (size_t i = 0; i < dev.size(); i++) a.inl[i] = dev[i];
-        } else {
-            CUDA_TRY(ctx, cudaMallocAsync(&d_pieces, dev.size() * sizeof(DevPiece), s));
-            CUDA_TRY(ctx, cudaMemcpyAsync(d_pieces, dev.data(), dev.size() * sizeof(DevPiece), cudaMemcpyHostToDevice, s));
-            a.pieces = d_pieces;
-        }
-        if (segs.size() <= (size_t)dmix::kInlineSegs) {
-            for (size_t i = 0; i < segs.size(); i++) a.inl_segs[i] = segs[i];
-        } else {
-            // segments + the coarse unit -> segment index in one allocation
-            const std::vector<uint32_t> index = build_seg_index(segs);
-            const size_t seg_bytes = segs.size() * sizeof(DevSeg);
-            CUDA_TRY(ctx, cudaMallocAsync(&d_segs, seg_bytes + index.size() * sizeof(uint32_t), s));
-            CUDA_TRY(ctx, cudaMemcpyAsync(d_segs, segs.data(), seg_bytes, cudaMemcpyHostToDevice, s));
-            CUDA_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(d_segs) + seg_bytes, index.data(), index.size() * sizeof(uint32_t),
-                                          cudaMemcpyHostToDevice, s));
-            a.segs = d_segs;
-            a.seg_index = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(d_segs) + seg_bytes);
-        }
         // persistent: one CTA per SM, every warp an independent pipeline over interleaved work units
         if (grid_only) a.nunits = nsamp / shape.tile_samples;   // whole tiles; the lean loop mixes the ragged end itself
         const uint32_t want = (a.nunits + shape.warps - 1) / shape.warps;
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->sm_count, want));
         const size_t smem = shape.fixed_smem + (smem_piece != dmix::kNoPiece ? shape.table_bytes(dev[smem_piece].period) : 0);
-        if (!grid_only) {
-            // work units are claimed from a counter: one per launch in flight, zeroed in stream order
-            a.unit_counter = ctx->unit_counters + (ctx->counter_next++ % kUnitCounters);
-            CUDA_TRY(ctx, cudaMemsetAsync(a.unit_counter, 0, sizeof(uint32_t), s));
+
+        // Launch metadata that does not fit the kernel parameters travels as ONE image -- [work-unit counter |
+        // pieces | segments | unit -> segment index] -- assembled in a pinned staging slot and sent with a single
+        // asynchronous copy (a track-mode launch carries ~10^3 pieces; separate pageable copies and a memset per
+        // launch cost ~10 % of a 600-piece launch).
+        const bool up_pieces = dev.size() > (size_t)dmix::kInlinePieces, up_segs = segs.size() > (size_t)dmix::kInlineSegs;
+        for (size_t i = 0; !up_pieces && i < dev.size(); i++) a.inl[i] = dev[i];
+        for (size_t i = 0; !up_segs && i < segs.size(); i++) a.inl_segs[i] = segs[i];
+        char* d_meta = nullptr;
+        MetaSlot* meta_slot = nullptr;
+        if (!grid_only || up_pieces) {
+            const std::vector<uint32_t> index = up_segs ? build_seg_index(segs) : std::vector<uint32_t>();
+            const size_t off_pieces = 16, off_segs = off_pieces + (up_pieces ? dev.size() * sizeof(DevPiece) : 0);
+            const size_t off_index = off_segs + (up_segs ? segs.size() * sizeof(DevSeg) : 0);
+            const size_t bytes = off_index + index.size() * sizeof(uint32_t);
+            MetaSlot& ms = ctx->meta[ctx->meta_next++ % kMetaSlots];
+            if (ms.used) CUDA_TRY(ctx, cudaEventSynchronize(ms.done));   // the launch that last used this slot has finished
+            if (ms.cap < bytes) {
+                if (ms.host) cudaFreeHost(ms.host);
+                if (ms.dev) cudaFree(ms.dev);
+                ms.host = ms.dev = nullptr;
+                ms.cap = 0;
+                const size_t cap = std::max<size_t>(bytes * 2, 1u << 16);
+                CUDA_TRY(ctx, cudaMallocHost(&ms.host, cap));
+                CUDA_TRY(ctx, cudaMalloc(&ms.dev, cap));
+                ms.cap = cap;
+            }
+            if (!ms.done) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ms.done, cudaEventDisableTiming));
+            char* h = static_cast<char*>(ms.host);
+            memset(h, 0, 16);   // the work-unit counter starts at 0
+            if (up_pieces) memcpy(h + off_pieces, dev.data(), dev.size() * sizeof(DevPiece));
+            if (up_segs) memcpy(h + off_segs, segs.data(), segs.size() * sizeof(DevSeg));
+            if (!index.empty()) memcpy(h + off_index, index.data(), index.size() * sizeof(uint32_t));
+            d_meta = static_cast<char*>(ms.dev);
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_meta, h, bytes, cudaMemcpyHostToDevice, s));
+            meta_slot = &ms;
+            a.unit_counter = reinterpret_cast<uint32_t*>(d_meta);
+            if (up_pieces) a.pieces = reinterpret_cast<const DevPiece*>(d_meta + off_pieces);
+            if (up_segs) {
+                a.segs = reinterpret_cast<const DevSeg*>(d_meta + off_segs);
+                a.seg_index = reinterpret_cast<const uint32_t*>(d_meta + off_index);
+            }
         }
         shape.kern<<<grid, shape.warps * 32, smem, s>>>(a);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
-        if (d_segs) CUDA_TRY(ctx, cudaFreeAsync(d_segs, s));
-        if (d_pieces) CUDA_TRY(ctx, cudaFreeAsync(d_pieces, s));
+        if (meta_slot) {
+            CUDA_TRY(ctx, cudaEventRecord(meta_slot->done, s));
+            meta_slot->used = true;
+        }
     }
     return DOPPLER_B200_OK;
 }
@@ -676,7 +702,6 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if (e2 == cudaSuccess) e2 = cudaMalloc(&ctx->unit_counters, kUnitCounters * sizeof(uint32_t));
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->tables_ready, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e2 == cudaSuccess; i++)
         for (int o = 0; o < 2 && e2 == cudaSuccess; o++) {
@@ -709,7 +734,11 @@ void doppler_b200_destroy(doppler_b200_ctx* ctx)
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     if (ctx->arena) cudaFree(ctx->arena);
-    if (ctx->unit_counters) cudaFree(ctx->unit_counters);
+    for (MetaSlot& ms : ctx->meta) {
+        if (ms.host) cudaFreeHost(ms.host);
+        if (ms.dev) cudaFree(ms.dev);
+        if (ms.done) cudaEventDestroy(ms.done);
+    }
     if (ctx->tables_ready) cudaEventDestroy(ctx->tables_ready);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -301,3 +301,22 @@ def test_column_segments_in_a_track_schedule(oracle, mixer):
         want, sn_ref = oracle.mix_blocks(buf, intype, outtype, shifts, fs)
         assert sn == sn_ref
         check(oracle, got, want, outtype)
+
+
+def test_random_schedules_all_type_pairs(oracle, mixer):
+    """Randomised per-block schedules (short / long / no reset periods mixed in one launch, arbitrary start
+    samplenum, ragged ends) through the planned entry point, all four type pairs."""
+    rng = np.random.default_rng(20151123)
+    pool = np.array([-9876.54, 7321.7, 5000.0, -3211.11, -15000.0, 0.0, 12_345.678, 1.0, 815000.0, -1234.5], dtype=np.float32)
+    for trial in range(12):
+        intype, outtype = TYPE_PAIRS[trial % 4]
+        fs = int(rng.choice([96_000, 1_024_000, 2_400_000]))
+        nruns = int(rng.integers(1, 6))
+        shifts = np.concatenate([np.repeat(rng.choice(pool), int(rng.integers(1, 400))) for _ in range(nruns)])
+        nbytes = shifts.size * BUFFER_SIZE - BPS[intype] * int(rng.integers(0, BUFFER_SIZE // BPS[intype]))
+        start = int(rng.choice([0, 1, 77_777, 2**24 + 5, 2**32 - 3]))
+        buf = make_input(rng, nbytes // BPS[intype], intype)
+        got, sn = mixer.mix_blocks(buf, intype, outtype, shifts, fs, samplenum=start)
+        want, sn_ref = oracle.mix_blocks(buf, intype, outtype, shifts, fs, samplenum=start)
+        assert sn == sn_ref, trial
+        check(oracle, got, want, outtype)

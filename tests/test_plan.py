@@ -157,3 +157,25 @@ def test_launch_tiles_track_schedule(oracle):
         trace, cover, tail, stats = dsp.plan_tiles_trace(it, ot, 0, shifts, block, fs, count)
         assert stats["column_segments"] >= 2, stats
         assert np.all(cover[:tail] == 1) and np.array_equal(trace[:tail], want[:tail])
+
+
+def test_launch_tiles_random_schedules(oracle):
+    """Randomised schedules (run lengths from one block to a few thousand, shifts drawn from values with short,
+    long and no reset periods, arbitrary start state and ragged ends): coverage and samplenum of the launch's
+    tiles against the planner's own trace (itself checked against the oracle above)."""
+    rng = np.random.default_rng(20151122)
+    pool = np.array([-9876.54, 7321.7, 5000.0, -3211.11, -15000.0, 0.0, 12_345.678, 1.0, 815000.0, -1234.5, 48000.0], dtype=np.float32)
+    for trial in range(24):
+        it, ot = [(dsp.I16, dsp.I16), (dsp.I16, dsp.F32), (dsp.F32, dsp.I16), (dsp.F32, dsp.F32)][trial % 4]
+        fs = int(rng.choice([96_000, 1_024_000, 2_400_000]))
+        block = 2048 if it == dsp.I16 else 1024
+        nruns = int(rng.integers(1, 7))
+        shifts = np.concatenate([np.repeat(rng.choice(pool), int(rng.integers(1, 1500))) for _ in range(nruns)])
+        count = int(shifts.size * block - rng.integers(0, block))
+        start = int(rng.choice([0, 1, 77_777, 2**24 + 5, 2**32 - 3]))
+        npipes = int(rng.choice([1, 13, 148 * 12]))
+        want, _, _ = dsp.plan_trace(start, shifts, block, fs, count)
+        trace, cover, tail, stats = dsp.plan_tiles_trace(it, ot, start, shifts, block, fs, count, npipes)
+        assert count - tail < 4, (trial, stats)
+        assert np.all(cover[:tail] == 1) and np.all(cover[tail:] == 0), (trial, stats)
+        assert np.array_equal(trace[:tail], want[:tail]), (trial, stats)
