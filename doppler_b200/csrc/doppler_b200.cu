@@ -22,7 +22,7 @@
 // (WARPS, S, U) of the segmented kernel per type pair, chosen on B200 (profiles/r01_seg_tune.md: warps
 // a multiple of the 4 schedulers, ~36-48 KB of loads in flight per SM, 12-16 samples per lane per tile so
 // that the per-tile pipeline overhead is amortised).  SEGV selects a tuning variant at build time
-// (`make variants`, tools/gpu_seg_tune.sh); the product is SEGV 0.
+// (`make variants`, tools/gpu/gpu_seg_tune.sh); the product is SEGV 0.
 #ifndef SEGV
 #define SEGV 0
 #endif

@@ -1,6 +1,6 @@
 #!/bin/bash
-# tools/gpu_session.sh -- one gpurun call: smoke, GPU parity tests, bench, ncu launch list + full capture.
-# Usage (from the repo root, on the GPU box): bash tools/gpu_session.sh [tag]
+# tools/gpu/gpu_session.sh -- one gpurun call: smoke, GPU parity tests, bench, ncu launch list + full capture.
+# Usage (from the repo root, on the GPU box): bash tools/gpu/gpu_session.sh [tag]
 TAG=${1:-r01}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
