@@ -143,18 +143,37 @@ __device__ __noinline__ float2 phasor(float r, uint32_t n)
     return make_float2(sc.c, sc.s);
 }
 
-// sample * corrector, num-complex 0.1.35 Mul: (a*c - b*d, a*d + b*c), four products and two
-// sums, each rounded separately (rustc never fuses).
-__device__ __forceinline__ float2 cmul_unfused(float2 smp, float2 ph)
+// Packed fp32 (sm_100 FMUL2): two independent IEEE round-to-nearest multiplies per issued instruction.
+// Only the MULTIPLIES are packed: ptxas contracts add.rn.f32x2 with a preceding mul.rn.f32x2 into FFMA2
+// even under --fmad=false, which would break the reference's unfused arithmetic, so sums stay scalar.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi)
 {
-    const float ac = __fmul_rn(smp.x, ph.x);
-    const float bd = __fmul_rn(smp.y, ph.y);
-    const float ad = __fmul_rn(smp.x, ph.y);
-    const float bc = __fmul_rn(smp.y, ph.x);
-    return make_float2(__fsub_rn(ac, bd), __fadd_rn(ad, bc));
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
 }
 
-// dsp.rs:91-92: (i16 as f32) / 32768.   (exact: power-of-two scale)
+// sample * corrector, num-complex 0.1.35 Mul: (a*c - b*d, a*d + b*c), four products and two
+// sums, each rounded separately (rustc never fuses).  The products are formed pairwise,
+// [a*c, b*c] and [b*(-d), a*d]; b*(-d) == -(b*d) and x + (-y) == x - y exactly in IEEE-754.
+__device__ __forceinline__ float2 cmul_unfused(float2 smp, float2 ph)
+{
+    float ac, bc, nbd, ad;
+    unpack_f32x2(mul_f32x2(pack_f32x2(smp.x, smp.y), pack_f32x2(ph.x, ph.x)), ac, bc);
+    unpack_f32x2(mul_f32x2(pack_f32x2(smp.y, smp.x), pack_f32x2(-ph.y, ph.y)), nbd, ad);
+    return make_float2(__fadd_rn(ac, nbd), __fadd_rn(ad, bc));
+}
+
 // i16 -> f32 of the low / high half of an IQ word without the slow-pipe I2F.S16 (measured ~4.5
 // issue cycles per warp against ~1.7 for LOP3 / FADD / I2FP, profiles/r01_pipes.jsonl):
 // low half by exponent bias, (2^23 + 2^15 + i) - (2^23 + 2^15), exact for every i16; high half by
@@ -165,6 +184,7 @@ __device__ __forceinline__ float i16_lo_f32(uint32_t w)
 }
 __device__ __forceinline__ float i16_hi_f32(uint32_t w) { return __int2float_rn((int)w >> 16); }
 
+// dsp.rs:91-92: (i16 as f32) / 32768.   (exact: power-of-two scale)
 __device__ __forceinline__ float2 ingest_i16(uint32_t w)
 {
     return make_float2(__fmul_rn(i16_lo_f32(w), 0x1p-15f), __fmul_rn(i16_hi_f32(w), 0x1p-15f));
@@ -175,8 +195,8 @@ __device__ __forceinline__ float2 ingest_i16(uint32_t w)
 __device__ __forceinline__ uint32_t egress_i16(float2 v)
 {
     short i, q;
-    const float fi = __fmul_rn(v.x, 32767.0f);
-    const float fq = __fmul_rn(v.y, 32767.0f);
+    float fi, fq;
+    unpack_f32x2(mul_f32x2(pack_f32x2(v.x, v.y), pack_f32x2(32767.0f, 32767.0f)), fi, fq);
     asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(i) : "f"(fi));
     asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(q) : "f"(fq));
     return (uint32_t)(uint16_t)i | ((uint32_t)(uint16_t)q << 16);
@@ -509,8 +529,8 @@ __device__ __forceinline__ uint32_t egress_i16_scaled(float2 v)
 {
     if constexpr (Scaling<IN, OUT>::kDeferred) {
         short i, q;
-        const float fi = __fmul_rn(v.x, 0x1.fffcp-1f /* 32767 * 2^-15 */);
-        const float fq = __fmul_rn(v.y, 0x1.fffcp-1f);
+        float fi, fq;
+        unpack_f32x2(mul_f32x2(pack_f32x2(v.x, v.y), pack_f32x2(0x1.fffcp-1f, 0x1.fffcp-1f /* 32767 * 2^-15 */)), fi, fq);
         asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(i) : "f"(fi));
         asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(q) : "f"(fq));
         return (uint32_t)(uint16_t)i | ((uint32_t)(uint16_t)q << 16);
