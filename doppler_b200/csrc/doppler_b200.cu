@@ -20,29 +20,29 @@
 #include "plan.h"
 
 // (WARPS, S, U) of the segmented kernel per type pair, chosen on B200 (profiles/r01_seg_tune.md: warps
-// a multiple of the 4 schedulers, ~36-48 KB of loads in flight per SM, 12-16 samples per lane per tile so
-// that the per-tile pipeline overhead is amortised).  SEGV selects a tuning variant at build time
+// a multiple of the 4 schedulers, 12-16 samples per lane per tile so that the per-tile pipeline overhead is
+// amortised; i16->i16 is issue-bound and wants 16 warps, which leaves room for a ~2600-entry table only).  SEGV selects a tuning variant at build time
 // (`make variants`, tools/gpu/gpu_seg_tune.sh); the product is SEGV 0.
 #ifndef SEGV
 #define SEGV 0
 #endif
 #if SEGV == 1
+#define SEG_I16I16 16, 2, 4
+#define SEG_I16F32 16, 3, 4
+#define SEG_F32I16 16, 2, 4
+#define SEG_F32F32 16, 2, 4
+#elif SEGV == 2
 #define SEG_I16I16 16, 2, 3
 #define SEG_I16F32 16, 3, 3
-#define SEG_F32I16 16, 2, 3
-#define SEG_F32F32 16, 2, 2
-#elif SEGV == 2
-#define SEG_I16I16 12, 2, 5
-#define SEG_I16F32 12, 3, 5
-#define SEG_F32I16 12, 2, 4
-#define SEG_F32F32 12, 2, 4
-#elif SEGV == 3
-#define SEG_I16I16 8, 2, 6
-#define SEG_I16F32 12, 2, 4
-#define SEG_F32I16 16, 2, 4
+#define SEG_F32I16 20, 2, 3
 #define SEG_F32F32 16, 2, 3
+#elif SEGV == 3
+#define SEG_I16I16 16, 3, 3
+#define SEG_I16F32 12, 3, 4
+#define SEG_F32I16 16, 2, 4
+#define SEG_F32F32 12, 2, 4
 #else
-#define SEG_I16I16 12, 2, 4
+#define SEG_I16I16 16, 2, 4
 #define SEG_I16F32 12, 3, 4
 #define SEG_F32I16 16, 2, 4
 #define SEG_F32F32 12, 2, 4
@@ -148,6 +148,7 @@ struct KernShape {
     uint32_t tile_samples, row_samples, gran;
     uint32_t fixed_smem;
     uint32_t (*table_bytes)(uint32_t period);
+    uint32_t smem_tab_entries;   // longest period whose table this kernel stages in shared memory
 };
 // Per (intype, outtype): the lean loop for a launch that is one GRID segment (const mode), and the
 // segmented loop (GRID + COLUMN segments) with its own, larger tile.
@@ -155,12 +156,23 @@ struct StreamShape {
     KernShape grid, seg;
 };
 
+// Longest period whose de-interleaved table (period + one row + padding entries of 8 bytes) still fits
+// next to the kernel's rings in the 227 KB of shared memory a CTA may have; at most kSmemTabMaxEntries.
+constexpr uint32_t smem_tab_capacity(uint32_t fixed_smem, uint32_t row_samples)
+{
+    const uint32_t budget = 227u * 1024u, slack = row_samples + 16u;
+    if (fixed_smem + (slack + 256u) * 8u >= budget) return 0;
+    const uint32_t fit = (budget - fixed_smem) / 8u - slack;
+    return fit < kSmemTabMaxEntries ? fit : kSmemTabMaxEntries;
+}
+
 template <int IN, int OUT, int WARPS, int S, int U, bool SEG>
 KernShape make_shape()
 {
     using C = dmix::StreamCfg<IN, OUT, WARPS, S, U>;
     return KernShape{SEG ? dmix::mix_stream_kernel<IN, OUT, WARPS, S, U> : dmix::mix_grid_kernel<IN, OUT, WARPS, S, U>, WARPS,
-                     (uint32_t)C::kTileSamples, (uint32_t)C::kRow, (uint32_t)C::kGran, (uint32_t)C::kFixedSmem, &C::table_bytes};
+                     (uint32_t)C::kTileSamples, (uint32_t)C::kRow, (uint32_t)C::kGran, (uint32_t)C::kFixedSmem, &C::table_bytes,
+                     smem_tab_capacity((uint32_t)C::kFixedSmem, (uint32_t)C::kRow)};
 }
 
 // (WARPS, S, U) of the segmented kernel per type pair; the host walk of the work decomposition
@@ -447,8 +459,6 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         }
         // get_table may have recycled the arena: offsets taken earlier in this launch would
         // dangle.  Re-resolve every tabled piece against the final cache (cheap, rare).
-        uint32_t smem_piece = dmix::kNoPiece;
-        uint64_t smem_piece_len = 0;
         for (size_t i = 0; i < dev.size(); i++) {
             DevPiece& d = dev[i];
             if (d.tab == dmix::kNoTab) continue;
@@ -456,11 +466,6 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
             memcpy(&key, &d.r, 4);
             auto it = ctx->tables.find(key);
             d.tab = (it != ctx->tables.end() && it->second.period == d.period) ? it->second.off : dmix::kNoTab;
-            // one table per launch is staged in shared memory: the eligible piece covering most samples
-            if (d.tab != dmix::kNoTab && d.period <= kSmemTabMaxEntries && dev_len[i] > smem_piece_len) {
-                smem_piece = (uint32_t)i;
-                smem_piece_len = dev_len[i];
-            }
         }
 
         const uint32_t nsamp = (uint32_t)(l1 - l0);
@@ -470,6 +475,14 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         // no COLUMN segment: the whole launch is one GRID segment and takes the lean loop
         const bool grid_only = segs.size() <= 1 && (segs.empty() || segs[0].rows == 0);
         const KernShape& shape = grid_only ? shapes.grid : shapes.seg;
+        // one table per launch is staged in shared memory: the eligible piece covering most samples
+        uint32_t smem_piece = dmix::kNoPiece;
+        uint64_t smem_piece_len = 0;
+        for (size_t i = 0; i < dev.size(); i++)
+            if (dev[i].tab != dmix::kNoTab && dev[i].period <= shape.smem_tab_entries && dev_len[i] > smem_piece_len) {
+                smem_piece = (uint32_t)i;
+                smem_piece_len = dev_len[i];
+            }
 
         MixArgs a;
         memset(&a, 0, sizeof a);
@@ -709,7 +722,7 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
             for (const KernShape* k : {&sh.grid, &sh.seg})
                 if (e2 == cudaSuccess)
                     e2 = cudaFuncSetAttribute(k->kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)(k->fixed_smem + k->table_bytes(kSmemTabMaxEntries)));
+                                              (int)(k->fixed_smem + k->table_bytes(k->smem_tab_entries)));
         }
     if (e2 != cudaSuccess) {
         fail(nullptr, DOPPLER_B200_ECUDA, "context setup failed: %s", cudaGetErrorString(e2));

@@ -3,7 +3,7 @@
 TAG=${1:-r01k}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-ONLY="P=111145,P=4.9M,cfg3 track,cfg4 track"
+ONLY="P=111145,cfg3 track,cfg4 track"
 echo "== product sweep"; timeout 900 python tools/sweep.py --only "$ONLY" --out $OUT/sweep_v0.jsonl > $OUT/sweep_v0.log 2>&1; echo "rc=$?"; cat $OUT/sweep_v0.log
 for v in 1 2 3; do
   export DOPPLER_B200_LIB=doppler_b200/libdoppler_b200_segv$v.so
