@@ -320,3 +320,23 @@ def test_random_schedules_all_type_pairs(oracle, mixer):
         want, sn_ref = oracle.mix_blocks(buf, intype, outtype, shifts, fs, samplenum=start)
         assert sn == sn_ref, trial
         check(oracle, got, want, outtype)
+
+
+def test_host_path_multi_chunk_with_long_periods(oracle, mixer):
+    """Host-buffer entry point over several 32 MiB pipeline chunks: every chunk is planned on its own (pieces
+    clipped at the chunk, COLUMN segments rebuilt, samplenum carried), the bytes must not show the seams."""
+    rng = np.random.default_rng(31)
+    n = 19_000_003                       # 76 MB of i16 input: three chunks, ragged end
+    buf = make_input(rng, n, I16)
+    for shift, fs in [(-9876.54, 1_024_000), (-15000.0, 256000)]:
+        got, sn = mixer.mix(buf, I16, I16, shift, fs, samplenum=3)
+        want, sn_ref = oracle.mix(buf, I16, I16, shift, fs, samplenum=3)
+        assert sn == sn_ref
+        check(oracle, got, want, I16)
+    per_sec = 1_024_000 * 4 // BUFFER_SIZE
+    shifts = np.concatenate([np.repeat(np.float32(s), per_sec) for s in np.linspace(-9000.0, 9000.0, 19)])
+    nbytes = min(buf.size, shifts.size * BUFFER_SIZE - 4 * 123)
+    got, sn = mixer.mix_blocks(buf[:nbytes], I16, F32, shifts, 1_024_000)
+    want, sn_ref = oracle.mix_blocks(buf[:nbytes], I16, F32, shifts, 1_024_000)
+    assert sn == sn_ref
+    check(oracle, got, want, F32)
