@@ -930,20 +930,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
     TileDesc* desc_ring = reinterpret_cast<TileDesc*>(descs + warp * C::kDescBytes);
     float2* win = reinterpret_cast<float2*>(wins + warp * C::kWinBytes);
 
-    // start-up: barriers + (optionally) one piece's table de-interleaved into shared memory
-    uint32_t plane_len = 0;
-    if (a.smem_piece != kNoPiece) {
-        const DevPiece sp = get_piece(a, a.smem_piece);
-        plane_len = C::plane_len(sp.period);
-        const float2* src = a.tables + sp.tab;
-        for (uint32_t e = threadIdx.x; e < sp.period + (uint32_t)C::kRow; e += WARPS * 32)
-            tab_s[(e % G) * plane_len + e / G] = __ldg(src + e % sp.period);   // replicated past the period: no wrap in a row
-    }
+    // start-up: every warp owns its barriers (lane 0 initialises them, issues on them, the warp waits on them),
+    // so the first loads go out before the CTA stages the table: their latency hides the staging
     if (lane == 0) {
         for (int s = 0; s < S; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncwarp();
 
     const uint32_t pipe = blockIdx.x * WARPS + warp, npipes = gridDim.x * WARPS;
     const unsigned char* gin = static_cast<const unsigned char*>(a.in);
@@ -966,6 +959,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
     };
     if (lane == 0)
         for (uint32_t s = 0; s < (uint32_t)S; s++) issue_next(s);
+
+    // (optionally) one piece's table de-interleaved into shared memory
+    uint32_t plane_len = 0;
+    if (a.smem_piece != kNoPiece) {
+        const DevPiece sp = get_piece(a, a.smem_piece);
+        plane_len = C::plane_len(sp.period);
+        const float2* src = a.tables + sp.tab;
+        for (uint32_t e = threadIdx.x; e < sp.period + (uint32_t)C::kRow; e += WARPS * 32)
+            tab_s[(e % G) * plane_len + e / G] = __ldg(src + e % sp.period);   // replicated past the period: no wrap in a row
+    }
+    __syncthreads();
 
     uint32_t pi = 0;                 // GRID: cached piece
     DevPiece p = get_piece(a, 0);
@@ -1070,20 +1074,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_grid_kernel(const __grid_co
     unsigned char* ring_in = rings + warp * C::kRing;
     unsigned char* ring_out = ring_in + S * C::kTileIn;
 
-    // start-up: barriers + (optionally) one piece's table de-interleaved into shared memory
-    uint32_t plane_len = 0;
-    if (a.smem_piece != kNoPiece) {
-        const DevPiece sp = get_piece(a, a.smem_piece);
-        plane_len = C::plane_len(sp.period);
-        const float2* src = a.tables + sp.tab;
-        for (uint32_t e = threadIdx.x; e < sp.period + (uint32_t)C::kRow; e += WARPS * 32)
-            tab_s[(e % G) * plane_len + e / G] = __ldg(src + e % sp.period);   // replicated past the period: no wrap in a row
-    }
+    // start-up: every warp owns its barriers (lane 0 initialises them, issues on them, the warp waits on them),
+    // so the first loads go out before the CTA stages the table: their latency hides the staging
     if (lane == 0) {
         for (int s = 0; s < S; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncwarp();
 
     const uint32_t pipe = blockIdx.x * WARPS + warp, npipes = gridDim.x * WARPS;
     const uint32_t ntiles = a.nunits;   // one GRID segment of whole tiles: unit = tile
@@ -1098,6 +1095,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_grid_kernel(const __grid_co
     };
     if (lane == 0)
         for (uint32_t i = 0; i < (uint32_t)S && i < mine; i++) issue_load(i);
+
+    // (optionally) one piece's table de-interleaved into shared memory
+    uint32_t plane_len = 0;
+    if (a.smem_piece != kNoPiece) {
+        const DevPiece sp = get_piece(a, a.smem_piece);
+        plane_len = C::plane_len(sp.period);
+        const float2* src = a.tables + sp.tab;
+        for (uint32_t e = threadIdx.x; e < sp.period + (uint32_t)C::kRow; e += WARPS * 32)
+            tab_s[(e % G) * plane_len + e / G] = __ldg(src + e % sp.period);   // replicated past the period: no wrap in a row
+    }
+    __syncthreads();
 
     uint32_t pi = 0;
     DevPiece p = get_piece(a, 0);
