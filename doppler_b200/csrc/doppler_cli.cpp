@@ -5,7 +5,10 @@
 // short read, one shift per block in track mode, samplenum carried), but pumps the stream in large
 // chunks: a reader thread fills pinned buffers, the GPU mixes a whole chunk per call
 // (doppler_b200_mix / doppler_b200_mix_blocks reproduce the per-block chain internally), a writer
-// thread drains.  stdout is byte-identical to the reference's for the same stdin.
+// thread drains.  stdout is byte-identical to the reference's for the same stdin.  Chunks are
+// ADAPTIVE: the reader dispatches what has arrived (whole blocks) as soon as stdin goes idle for
+// kIdleMicros, so a live 1 Msps pipe sees millisecond latency (the reference: one 8 KiB block) while
+// a fast producer fills 32 MiB chunks.
 //
 // Extensions (not in the reference): --device N; --doppler-table FILE (track replay from a text
 // file of doppler_hz values, one per second of recording, instead of --tlefile/--tlename/
@@ -17,6 +20,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
+#include <poll.h>
 #include <sys/time.h>
 #include <time.h>
 #include <unistd.h>
@@ -34,7 +39,8 @@ namespace {
 
 const char* kVersion = "1.1.10-b200";
 constexpr size_t kBlock = DOPPLER_B200_BUFFER_SIZE;
-constexpr size_t kChunkBlocks = 4096;   // 32 MiB of input per GPU call
+constexpr size_t kChunkBlocks = 4096;   // 32 MiB of input per GPU call, at most
+constexpr long kIdleMicros = 500;       // stdin idle for this long: dispatch what has arrived
 
 // src/main.rs:212-233: "<time>.<ms> [<level> <module> <line>]  <msg>" on stderr
 void logline(const char* level, int line, const char* fmt, ...)
@@ -325,6 +331,39 @@ size_t read_full(int fd, uint8_t* buf, size_t want)
     return got;
 }
 
+// One adaptive chunk: block until one whole block is there (or EOF), keep taking what arrives while stdin
+// stays busy (gaps shorter than kIdleMicros) up to `cap`, then complete the last block so that every chunk
+// but the stream's last is a whole number of blocks.  *eof is set when the stream ended.
+size_t read_chunk(int fd, uint8_t* buf, size_t cap, bool* eof)
+{
+    size_t got = 0;
+    *eof = false;
+    auto take = [&](size_t want) {   // one blocking read of at most `want` bytes
+        for (;;) {
+            const ssize_t r = read(fd, buf + got, want);
+            if (r < 0) {
+                if (errno == EINTR) continue;
+                fprintf(stderr, "doppler collect error: %s\n", strerror(errno));   // main.rs:63 expect(...)
+                exit(101);
+            }
+            if (r == 0) *eof = true;
+            got += (size_t)r;
+            return;
+        }
+    };
+    while (!*eof && got < kBlock) take(cap - got);
+    while (!*eof && got < cap) {
+        struct pollfd pfd = {fd, POLLIN, 0};
+        struct timespec ts = {0, kIdleMicros * 1000};
+        const int pr = ppoll(&pfd, 1, &ts, nullptr);
+        if (pr == 0) break;              // idle: the producer is slower than we are
+        if (pr < 0 && errno != EINTR) break;
+        if (pr > 0) take(cap - got);
+    }
+    while (!*eof && got % kBlock != 0) take(kBlock - got % kBlock);
+    return got;
+}
+
 void write_full(int fd, const uint8_t* buf, size_t len)
 {
     size_t done = 0;
@@ -476,6 +515,10 @@ int main(int argc, char** argv)
             return 1;
         }
     }
+#ifdef F_SETPIPE_SZ
+    fcntl(0, F_SETPIPE_SZ, 1 << 20);   // fewer, larger reads / writes when stdin / stdout are pipes (best effort)
+    fcntl(1, F_SETPIPE_SZ, 1 << 20);
+#endif
     Channel free_q, filled_q, done_q, written_q;
     for (int i = 0; i < kBufs; i++) free_q.push(i);
 
@@ -483,8 +526,7 @@ int main(int argc, char** argv)
         for (;;) {
             const int i = free_q.pop();
             Chunk& c = chunks[i];
-            c.in_len = read_full(0, c.in, in_cap);
-            c.last = c.in_len != in_cap;   // a short read ends the stream (main.rs:98)
+            c.in_len = read_chunk(0, c.in, in_cap, &c.last);   // the stream ends at the first short block (main.rs:98)
             filled_q.push(i);
             if (c.last) break;
         }
@@ -503,7 +545,9 @@ int main(int argc, char** argv)
 
     const ReplayClock clock{args.samplerate, kBlock / ibps};
     std::vector<float> shifts;
-    uint64_t block0 = 0;
+    uint64_t block0 = 0, bytes_in = 0, nchunks = 0;
+    struct timeval pump_t0;
+    gettimeofday(&pump_t0, nullptr);
     int64_t last_logged_second = 0;
     int exit_code = 0;
     for (;;) {
@@ -519,6 +563,8 @@ int main(int argc, char** argv)
             panic = true;
         }
         c.out_len = 0;
+        bytes_in += c.in_len;
+        nchunks++;
         if (!args.track) {
             rc = doppler_b200_mix(ctx, c.in, usable, args.intype, args.outtype, (float)args.shift /* main.rs:110 */, args.samplerate,
                                   &samplenr, c.out, out_cap, &c.out_len);
@@ -551,7 +597,7 @@ int main(int argc, char** argv)
                                              &samplenr, c.out, out_cap, &c.out_len);
                 if (rc) die_ctx(ctx, "doppler_b200_mix_blocks", rc);
             }
-            block0 += kChunkBlocks;
+            block0 += nblocks;
         }
         const bool last = c.last;
         done_q.push(i);
@@ -563,6 +609,13 @@ int main(int argc, char** argv)
     }
     reader.join();
     writer.join();
+    if (getenv("DOPPLER_STATS")) {   // not in the reference: pump statistics for tools/cli_bench.sh
+        struct timeval t1;
+        gettimeofday(&t1, nullptr);
+        const double sec = (double)(t1.tv_sec - pump_t0.tv_sec) + 1e-6 * (double)(t1.tv_usec - pump_t0.tv_usec);
+        fprintf(stderr, "{\"pump_bytes_in\": %llu, \"pump_seconds\": %.6f, \"chunks\": %llu, \"in_MBps\": %.1f}\n",
+                (unsigned long long)bytes_in, sec, (unsigned long long)nchunks, sec > 0 ? 1e-6 * (double)bytes_in / sec : 0.0);
+    }
     if (exit_code == 101) fprintf(stderr, "thread 'main' panicked at 'assertion failed: inbuf.len() %% %zu == 0', src/dsp.rs\n", ibps);
     for (Chunk& c : chunks) {
         doppler_b200_host_free(c.in);

@@ -168,3 +168,53 @@ def test_track_replay_with_tle_matches_library_schedule(oracle, tmp_path):
     assert r.returncode == 0, r.stderr
     assert r.stdout == want.tobytes()
     assert b"range rate" in r.stderr   # main.rs:167-175 telemetry every 5 s of stream time
+
+
+@pytest.mark.gpu
+def test_live_pipe_latency_and_trickled_input(oracle):
+    """A live producer (rtl_fm at ~1 Msps) delivers a few blocks at a time: the pump must hand back what has
+    arrived within milliseconds (the reference: one 8192-byte block), not wait for a 32 MiB chunk -- and the
+    bytes must equal the one-shot result however the input is sliced into writes."""
+    import select
+    import time
+    n = 2048 * 40 + 777                                  # 40 blocks + a short last one
+    x = tone_i16(n, 1_024_000, 7).tobytes()
+    want, _, _ = oracle.const_stream(np.frombuffer(x, dtype=np.uint8), I16, I16, 5000, 1_024_000)
+    p = subprocess.Popen([CLI, "const", "-s", "1024000", "-i", "i16", "--shift", "5000"], stdin=subprocess.PIPE,
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, bufsize=0)
+    got = bytearray()
+    fd = p.stdout.fileno()
+    # first 3 blocks, then silence: their output must arrive while stdin is still open
+    p.stdin.write(x[:3 * BUFFER_SIZE])
+    deadline = time.time() + 30.0                        # generous: includes CUDA start-up
+    while len(got) < 3 * BUFFER_SIZE and time.time() < deadline:
+        if select.select([fd], [], [], 0.2)[0]:
+            got += os.read(fd, 1 << 20)
+    assert len(got) == 3 * BUFFER_SIZE, "output of the blocks already delivered did not arrive while stdin was idle"
+    # now a warm pump: one block at a time, each answered promptly
+    t_worst = 0.0
+    for b in range(3, 10):
+        t0 = time.time()
+        p.stdin.write(x[b * BUFFER_SIZE:(b + 1) * BUFFER_SIZE])
+        need = (b + 1) * BUFFER_SIZE
+        while len(got) < need and time.time() < t0 + 5.0:
+            if select.select([fd], [], [], 0.05)[0]:
+                got += os.read(fd, 1 << 20)
+        assert len(got) == need
+        t_worst = max(t_worst, time.time() - t0)
+    assert t_worst < 0.25, f"block latency {t_worst * 1e3:.1f} ms"
+    # the rest in odd-sized writes that do not respect block boundaries
+    k = 10 * BUFFER_SIZE
+    for step in (1, 8191, 8193, 30_000, 100_000):
+        p.stdin.write(x[k:k + step])
+        k += step
+        time.sleep(0.002)
+    p.stdin.write(x[k:])
+    p.stdin.close()
+    while True:
+        chunk = os.read(fd, 1 << 20)
+        if not chunk:
+            break
+        got += chunk
+    assert p.wait(timeout=30) == 0
+    assert bytes(got) == want.tobytes()
