@@ -22,6 +22,8 @@ SIGNATURES = {
     "doppler_b200_last_error": (ctypes.c_char_p, [c_ctx]),
     "doppler_b200_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "doppler_b200_host_free": (None, [ctypes.c_void_p]),
+    "doppler_b200_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
+    "doppler_b200_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
     "doppler_b200_launch_count": (ctypes.c_uint64, [c_ctx]),
     "doppler_b200_convert_iqi16_to_complex": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "doppler_b200_convert_iqf32_to_complex": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),

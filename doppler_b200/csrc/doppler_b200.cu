@@ -774,6 +774,26 @@ void doppler_b200_host_free(void* p)
     if (p) cudaFreeHost(p);
 }
 
+int doppler_b200_host_register(void* p, size_t bytes)
+{
+    if (!p || bytes == 0) return DOPPLER_B200_EINVAL;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return DOPPLER_B200_ECUDA;
+    }
+    return DOPPLER_B200_OK;
+}
+
+int doppler_b200_host_unregister(void* p)
+{
+    if (!p) return DOPPLER_B200_EINVAL;
+    if (cudaHostUnregister(p) != cudaSuccess) {
+        cudaGetLastError();
+        return DOPPLER_B200_ECUDA;
+    }
+    return DOPPLER_B200_OK;
+}
+
 uint64_t doppler_b200_launch_count(const doppler_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int doppler_b200_synchronize(doppler_b200_ctx* ctx)

@@ -457,12 +457,55 @@ int main(int argc, char** argv)
         INFO("\toffset          : %d Hz\n\n\n", args.offset);
     }
 
+    // ---- chunked modes (const, track replay): start draining stdin NOW, into page-aligned buffers that are
+    // pinned in place once the CUDA context exists.  Creating the context takes 1-3 s; a live producer
+    // (rtl_fm ...) must not find its pipe full for that long.
+    const bool chunked = !(args.track && !args.have_time);
+    constexpr int kBufs = 3;
+    const size_t in_cap = kChunkBlocks * kBlock, out_cap = in_cap / ibps * obps;
+    Chunk chunks[kBufs];
+    Channel free_q, filled_q, done_q;
+    std::thread reader;
+    if (chunked) {
+        for (Chunk& c : chunks) {
+            c.in = (uint8_t*)aligned_alloc(4096, in_cap);
+            c.out = (uint8_t*)aligned_alloc(4096, out_cap);
+            if (!c.in || !c.out) {
+                ERROR("host allocation failed");
+                return 1;
+            }
+        }
+#ifdef F_SETPIPE_SZ
+        fcntl(0, F_SETPIPE_SZ, 1 << 20);   // fewer, larger reads / writes when stdin / stdout are pipes (best effort)
+        fcntl(1, F_SETPIPE_SZ, 1 << 20);
+#endif
+        for (int i = 0; i < kBufs; i++) free_q.push(i);
+        reader = std::thread([&] {
+            for (;;) {
+                const int i = free_q.pop();
+                Chunk& c = chunks[i];
+                c.in_len = read_chunk(0, c.in, in_cap, &c.last);   // the stream ends at the first short block (main.rs:98)
+                filled_q.push(i);
+                if (c.last) break;
+            }
+        });
+    }
+
+    struct timeval t_start;
+    gettimeofday(&t_start, nullptr);
+    auto since_start_ms = [&] {
+        struct timeval t;
+        gettimeofday(&t, nullptr);
+        return 1e3 * (double)(t.tv_sec - t_start.tv_sec) + 1e-3 * (double)(t.tv_usec - t_start.tv_usec);
+    };
     doppler_b200_ctx* ctx = nullptr;
     int rc = doppler_b200_create(args.device, &ctx);
     if (rc != DOPPLER_B200_OK) {
         ERROR("doppler_b200_create failed (%d): %s", rc, doppler_b200_last_error(nullptr));
-        return 1;
+        fflush(stderr);
+        _exit(1);   // the reader thread may be blocked in read(2)
     }
+    const double ms_create = since_start_ms();
 
     uint32_t samplenr = 0;   // main.rs:60
 
@@ -504,33 +547,12 @@ int main(int argc, char** argv)
     }
 
     // ---- const mode and track replay: chunked pump, reader / GPU / writer overlapped ----
-    constexpr int kBufs = 3;
-    const size_t in_cap = kChunkBlocks * kBlock, out_cap = in_cap / ibps * obps;
-    Chunk chunks[kBufs];
-    for (Chunk& c : chunks) {
-        c.in = (uint8_t*)doppler_b200_host_alloc(in_cap);
-        c.out = (uint8_t*)doppler_b200_host_alloc(out_cap);
-        if (!c.in || !c.out) {
-            ERROR("pinned host allocation failed");
-            return 1;
-        }
-    }
-#ifdef F_SETPIPE_SZ
-    fcntl(0, F_SETPIPE_SZ, 1 << 20);   // fewer, larger reads / writes when stdin / stdout are pipes (best effort)
-    fcntl(1, F_SETPIPE_SZ, 1 << 20);
-#endif
-    Channel free_q, filled_q, done_q, written_q;
-    for (int i = 0; i < kBufs; i++) free_q.push(i);
+    for (Chunk& c : chunks)   // pin in place (the reader may already be filling them); unpinned still works, slower
+        if (doppler_b200_host_register(c.in, in_cap) != 0 || doppler_b200_host_register(c.out, out_cap) != 0)
+            INFO("could not pin the chunk buffers: %s", doppler_b200_last_error(ctx));
+    if (getenv("DOPPLER_STATS"))
+        fprintf(stderr, "{\"startup_ms_context\": %.1f, \"startup_ms_pinned_buffers\": %.1f}\n", ms_create, since_start_ms() - ms_create);
 
-    std::thread reader([&] {
-        for (;;) {
-            const int i = free_q.pop();
-            Chunk& c = chunks[i];
-            c.in_len = read_chunk(0, c.in, in_cap, &c.last);   // the stream ends at the first short block (main.rs:98)
-            filled_q.push(i);
-            if (c.last) break;
-        }
-    });
     std::thread writer([&] {
         for (;;) {
             const int i = done_q.pop();
@@ -618,8 +640,10 @@ int main(int argc, char** argv)
     }
     if (exit_code == 101) fprintf(stderr, "thread 'main' panicked at 'assertion failed: inbuf.len() %% %zu == 0', src/dsp.rs\n", ibps);
     for (Chunk& c : chunks) {
-        doppler_b200_host_free(c.in);
-        doppler_b200_host_free(c.out);
+        doppler_b200_host_unregister(c.in);
+        doppler_b200_host_unregister(c.out);
+        free(c.in);
+        free(c.out);
     }
     doppler_b200_destroy(ctx);
     return exit_code;

@@ -72,6 +72,11 @@ const char* doppler_b200_last_error(const doppler_b200_ctx* ctx);
 /* Pinned host memory (lets the host-buffer entry points DMA directly instead of staging). */
 void* doppler_b200_host_alloc(size_t bytes);
 void doppler_b200_host_free(void* p);
+/* Pins caller-owned, page-aligned host memory in place (cudaHostRegister) so that the host-buffer entry
+ * points copy from / to it directly; 0 on success.  The CLI uses it to start reading stdin before the
+ * CUDA context exists.  Unregister before freeing the memory. */
+int doppler_b200_host_register(void* p, size_t bytes);
+int doppler_b200_host_unregister(void* p);
 
 /* Number of kernel launches issued by this context so far (mixer + table builders). */
 uint64_t doppler_b200_launch_count(const doppler_b200_ctx* ctx);
