@@ -5,20 +5,20 @@
 // exp(-j*2*pi*(shift/fs)*samplenum) (src/dsp.rs:117-134), egress cast (src/main.rs:73-93).
 //
 // Layout in HBM: input and output are the reference's own interleaved little-endian IQ byte
-// streams (4 B/sample i16, 8 B/sample f32), 16-byte aligned.  Work is cut into TILES of
-// 256 threads x U groups x G samples; a thread's group is 8 or 16 contiguous bytes on the wide
-// side, consecutive lanes take consecutive groups, so every warp-level load/store instruction
-// covers one contiguous 256/512-byte span (fully coalesced, 128-bit where the format allows).
-// Each CTA walks a contiguous run of tiles.
+// streams (4 B/sample i16, 8 B/sample f32), 16-byte aligned.  Work is cut into TILES of U rows;
+// a row is one GROUP per lane (G samples = 8 or 16 contiguous bytes on the wide side), consecutive
+// lanes take consecutive groups.  Every warp is an independent cp.async.bulk pipeline over tiles
+// (mix_grid_kernel: const mode; mix_stream_kernel: GRID and COLUMN segments, track mode).
 //
 // The phase index is the reference's `samplenum` state machine, not the sample index.  The
 // host planner (plan.h) supplies PIECES in which samplenum is closed-form; a tile that lies
-// inside one piece takes a branch-free fast path, tiles that straddle pieces (or the ragged
-// tail) take a per-sample path.  The phasor comes either from a TABLE of the piece's period
-// (built once per shift by build_phasor_table_kernel with the same device routine, staged in
-// shared memory when it fits, read through L1/L2 otherwise) or from direct evaluation of the
-// bit-exact double-precision sincosf (sincosf_glibc.h).  A sin/cos recurrence is NOT used: the
-// reference quantises theta to f32 before the trig call, which no recurrence reproduces.
+// inside one piece takes a branch-free fast path, tiles that straddle pieces take a per-sample
+// path.  The phasor comes from a TABLE of the piece's period staged in shared memory (periods
+// up to 4096, built once per shift by build_phasor_table_kernel with the same device routine),
+// from a COLUMN window (long periods: evaluated once per column, reused over the rows of the
+// period structure), or from direct evaluation per sample of the bit-exact double-precision
+// sincosf (sincosf_glibc.h).  A sin/cos recurrence is NOT used: the reference quantises theta
+// to f32 before the trig call, which no recurrence reproduces.
 //
 // Roofline: HBM.  Algorithmic bytes per complex sample: i16->i16 8, i16->f32 12, f32->i16 12,
 // f32->f32 16 (table / piece traffic is O(period) and excluded).
@@ -30,8 +30,7 @@
 
 namespace dmix {
 
-constexpr int kThreads = 256;   // default CTA size (table builder, converters, default mixer config)
-constexpr int kUnroll = 4;      // default groups per thread per tile
+constexpr int kThreads = 256;   // CTA size of the table builder and the converters
 constexpr uint32_t kNoTab = 0xffffffffu;
 constexpr int kInlinePieces = 4;
 constexpr int kTabPad = 4;   // table entries replicated past the period (>= max group size)
@@ -41,10 +40,6 @@ constexpr int F32 = 1;
 
 // samples per thread-group: the side with the wider sample gets 16 bytes per lane
 __host__ __device__ constexpr int group_samples(int in, int out) { return (in == I16 && out == I16) ? 4 : 2; }
-__host__ __device__ constexpr uint32_t tile_samples(int in, int out, int threads = kThreads, int unroll = kUnroll)
-{
-    return (uint32_t)threads * unroll * group_samples(in, out);
-}
 
 struct DevPiece {          // launch-relative sample indices
     uint32_t k_begin;
@@ -120,10 +115,6 @@ struct MixArgs {
     uint32_t nsegs;
     uint32_t nunits;          // work units over all segments
     uint32_t tail_begin;      // samples [tail_begin, nsamples): the sub-granule end of the buffer
-    uint32_t ntiles;          // mix_kernel (tuning harness) only
-    uint32_t tiles_per_cta;   // mix_kernel only
-    uint32_t smem_entries;    // mix_kernel only
-    uint32_t interleave;      // mix_kernel only
     uint32_t smem_piece;      // streaming kernel: piece whose table is staged in shared memory, or kNoPiece
     DevPiece inl[kInlinePieces];
     DevSeg inl_segs[kInlineSegs];
@@ -203,42 +194,7 @@ __device__ __forceinline__ uint32_t egress_i16(float2 v)
 }
 
 // ---------------------------------------------------------------------------------------------
-// streaming group loads / stores (evict-first: every byte is touched once)
-template <int IN, int G>
-__device__ __forceinline__ void load_group(const void* in, uint32_t g, float2 (&s)[G])
-{
-    if constexpr (IN == I16 && G == 4) {
-        const uint4 w = __ldcs(reinterpret_cast<const uint4*>(in) + g);
-        s[0] = ingest_i16(w.x);
-        s[1] = ingest_i16(w.y);
-        s[2] = ingest_i16(w.z);
-        s[3] = ingest_i16(w.w);
-    } else if constexpr (IN == I16 && G == 2) {
-        const uint2 w = __ldcs(reinterpret_cast<const uint2*>(in) + g);
-        s[0] = ingest_i16(w.x);
-        s[1] = ingest_i16(w.y);
-    } else {
-        static_assert(G == 2, "f32 input groups are 2 samples");
-        const float4 w = __ldcs(reinterpret_cast<const float4*>(in) + g);
-        s[0] = make_float2(w.x, w.y);
-        s[1] = make_float2(w.z, w.w);
-    }
-}
-
-template <int OUT, int G>
-__device__ __forceinline__ void store_group(void* out, uint32_t g, const float2 (&v)[G])
-{
-    if constexpr (OUT == I16 && G == 4) {
-        __stcs(reinterpret_cast<uint4*>(out) + g,
-               make_uint4(egress_i16(v[0]), egress_i16(v[1]), egress_i16(v[2]), egress_i16(v[3])));
-    } else if constexpr (OUT == I16 && G == 2) {
-        __stcs(reinterpret_cast<uint2*>(out) + g, make_uint2(egress_i16(v[0]), egress_i16(v[1])));
-    } else {
-        static_assert(G == 2, "f32 output groups are 2 samples");
-        __stcs(reinterpret_cast<float4*>(out) + g, make_float4(v[0].x, v[0].y, v[1].x, v[1].y));
-    }
-}
-
+// single-sample streaming loads / stores (ragged ends, converters)
 template <int IN>
 __device__ __forceinline__ float2 load_sample(const void* in, uint32_t k)
 {
@@ -295,118 +251,7 @@ __device__ __forceinline__ uint32_t piece_samplenum(const DevPiece& p, uint32_t 
     return x - q * p.period + 1u;
 }
 
-enum FastMode { kTabShared = 0, kTabGlobal = 1, kDirectPeriodic = 2, kDirectLinear = 3 };
-
-// A full tile inside one piece.  All U group loads are issued before any arithmetic.
-template <int IN, int OUT, int MODE, int T, int U>
-__device__ __forceinline__ void fast_tile(const MixArgs& a, const DevPiece& p, uint32_t k0, const float2* tab)
-{
-    constexpr int G = group_samples(IN, OUT);
-    const uint32_t g0 = k0 / G + threadIdx.x;
-    float2 smp[U][G];
-#pragma unroll
-    for (int u = 0; u < U; u++) load_group<IN, G>(a.in, g0 + u * T, smp[u]);
-
-    const uint32_t off = (k0 - p.k_begin) + threadIdx.x * G;
-    uint32_t j = 0;
-    if constexpr (MODE != kDirectLinear) j = piece_samplenum(p, off) - 1u;   // phase index in [0, period)
-
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-        float2 res[G];
-#pragma unroll
-        for (int s = 0; s < G; s++) {
-            float2 ph;
-            if constexpr (MODE == kTabShared) {
-                ph = tab[j + s];                    // padded: no wrap inside a group
-            } else if constexpr (MODE == kTabGlobal) {
-                ph = __ldg(tab + j + s);
-            } else if constexpr (MODE == kDirectPeriodic) {
-                uint32_t n = j + s + 1u;
-                if (n > p.period) n -= p.period;
-                ph = phasor(p.r, n);
-            } else {
-                ph = phasor(p.r, p.base + off + (uint32_t)(u * T * G + s));
-            }
-            res[s] = cmul_unfused(smp[u][s], ph);
-        }
-        store_group<OUT, G>(a.out, g0 + u * T, res);
-        if constexpr (MODE != kDirectLinear) {
-            j += p.step_u;
-            if (j >= p.period) j -= p.period;
-        }
-    }
-}
-
-// Generic per-sample tile: piece boundaries inside the tile and/or the ragged end of the buffer.
-template <int IN, int OUT, int T, int U>
-__device__ __noinline__ void slow_tile(const MixArgs& a, uint32_t pi, uint32_t k0)
-{
-    constexpr uint32_t kTile = tile_samples(IN, OUT, T, U);
-    DevPiece p = get_piece(a, pi);
-    for (uint32_t i = threadIdx.x; i < kTile; i += T) {
-        const uint32_t k = k0 + i;
-        if (k >= a.nsamples) break;
-        if (k >= p.k_end) {
-            pi = find_piece(a, pi, k);
-            p = get_piece(a, pi);
-        }
-        const uint32_t n = piece_samplenum(p, k - p.k_begin);
-        const float2 ph = phasor(p.r, n);
-        store_sample<OUT>(a.out, k, cmul_unfused(load_sample<IN>(a.in, k), ph));
-    }
-}
-
-// T threads per CTA, U groups per thread per tile, at least MINB resident CTAs per SM.
-template <int IN, int OUT, int T = kThreads, int U = kUnroll, int MINB = 0>
-__global__ void __launch_bounds__(T, MINB) mix_kernel(const __grid_constant__ MixArgs a)
-{
-    constexpr uint32_t kTile = tile_samples(IN, OUT, T, U);
-    extern __shared__ float2 tab_s[];
-
-    uint32_t tile, tile_end, tile_step;
-    if (a.interleave) {
-        tile = blockIdx.x;
-        tile_end = a.ntiles;
-        tile_step = gridDim.x;
-    } else {
-        tile = blockIdx.x * a.tiles_per_cta;
-        tile_end = min(tile + a.tiles_per_cta, a.ntiles);
-        tile_step = 1;
-    }
-    uint32_t pi = 0;
-    uint32_t staged = 0xffffffffu;   // piece whose table is in shared memory
-    DevPiece p = get_piece(a, 0);
-
-    for (; tile < tile_end; tile += tile_step) {
-        const uint32_t k0 = tile * kTile;
-        if (k0 >= p.k_end) {
-            pi = find_piece(a, pi, k0);
-            p = get_piece(a, pi);
-        }
-        const bool fast = (k0 + kTile <= p.k_end) && (k0 + kTile <= a.nsamples);
-        if (!fast) {
-            slow_tile<IN, OUT, T, U>(a, pi, k0);
-            continue;
-        }
-        if (p.period == 0) {
-            fast_tile<IN, OUT, kDirectLinear, T, U>(a, p, k0, nullptr);
-        } else if (p.tab == kNoTab) {
-            fast_tile<IN, OUT, kDirectPeriodic, T, U>(a, p, k0, nullptr);
-        } else if (p.period <= a.smem_entries) {
-            if (staged != pi) {            // CTA-uniform
-                __syncthreads();
-                for (uint32_t e = threadIdx.x; e < p.period + kTabPad; e += T)
-                    tab_s[e] = __ldg(a.tables + p.tab + e);
-                __syncthreads();
-                staged = pi;
-            }
-            fast_tile<IN, OUT, kTabShared, T, U>(a, p, k0, tab_s);
-        } else {
-            fast_tile<IN, OUT, kTabGlobal, T, U>(a, p, k0, a.tables + p.tab);
-        }
-    }
-}
+enum FastMode { kTabShared = 0, kTabGlobal = 1 };   // phasor table staged in shared memory / read through L1-L2
 
 // =============================================================================================
 // Streaming kernel: every warp is an independent bulk-async (TMA 1-D) pipeline.

@@ -27,6 +27,171 @@
         }                                                                                       \
     } while (0)
 
+
+// ---------------------------------------------------------------------------------------------
+// The round-1 "v0" register-staged kernel (LDG -> registers -> STG), kept here only as the baseline
+// the bulk-async pipelines are measured against; it is not part of the product any more.
+namespace dmix {
+constexpr int kUnroll = 4;
+__host__ __device__ constexpr uint32_t tile_samples(int in, int out, int threads = kThreads, int unroll = kUnroll)
+{
+    return (uint32_t)threads * unroll * group_samples(in, out);
+}
+enum LegacyMode { kLegacyTabShared = 0, kLegacyTabGlobal = 1, kDirectPeriodic = 2, kDirectLinear = 3 };
+struct LegacyArgs : MixArgs {
+    uint32_t ntiles, tiles_per_cta, smem_entries, interleave;
+};
+// ---------------------------------------------------------------------------------------------
+// streaming group loads / stores (evict-first: every byte is touched once)
+template <int IN, int G>
+__device__ __forceinline__ void load_group(const void* in, uint32_t g, float2 (&s)[G])
+{
+    if constexpr (IN == I16 && G == 4) {
+        const uint4 w = __ldcs(reinterpret_cast<const uint4*>(in) + g);
+        s[0] = ingest_i16(w.x);
+        s[1] = ingest_i16(w.y);
+        s[2] = ingest_i16(w.z);
+        s[3] = ingest_i16(w.w);
+    } else if constexpr (IN == I16 && G == 2) {
+        const uint2 w = __ldcs(reinterpret_cast<const uint2*>(in) + g);
+        s[0] = ingest_i16(w.x);
+        s[1] = ingest_i16(w.y);
+    } else {
+        static_assert(G == 2, "f32 input groups are 2 samples");
+        const float4 w = __ldcs(reinterpret_cast<const float4*>(in) + g);
+        s[0] = make_float2(w.x, w.y);
+        s[1] = make_float2(w.z, w.w);
+    }
+}
+
+template <int OUT, int G>
+__device__ __forceinline__ void store_group(void* out, uint32_t g, const float2 (&v)[G])
+{
+    if constexpr (OUT == I16 && G == 4) {
+        __stcs(reinterpret_cast<uint4*>(out) + g,
+               make_uint4(egress_i16(v[0]), egress_i16(v[1]), egress_i16(v[2]), egress_i16(v[3])));
+    } else if constexpr (OUT == I16 && G == 2) {
+        __stcs(reinterpret_cast<uint2*>(out) + g, make_uint2(egress_i16(v[0]), egress_i16(v[1])));
+    } else {
+        static_assert(G == 2, "f32 output groups are 2 samples");
+        __stcs(reinterpret_cast<float4*>(out) + g, make_float4(v[0].x, v[0].y, v[1].x, v[1].y));
+    }
+}
+
+// A full tile inside one piece.  All U group loads are issued before any arithmetic.
+template <int IN, int OUT, int MODE, int T, int U>
+__device__ __forceinline__ void fast_tile(const LegacyArgs& a, const DevPiece& p, uint32_t k0, const float2* tab)
+{
+    constexpr int G = group_samples(IN, OUT);
+    const uint32_t g0 = k0 / G + threadIdx.x;
+    float2 smp[U][G];
+#pragma unroll
+    for (int u = 0; u < U; u++) load_group<IN, G>(a.in, g0 + u * T, smp[u]);
+
+    const uint32_t off = (k0 - p.k_begin) + threadIdx.x * G;
+    uint32_t j = 0;
+    if constexpr (MODE != kDirectLinear) j = piece_samplenum(p, off) - 1u;   // phase index in [0, period)
+
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        float2 res[G];
+#pragma unroll
+        for (int s = 0; s < G; s++) {
+            float2 ph;
+            if constexpr (MODE == kLegacyTabShared) {
+                ph = tab[j + s];                    // padded: no wrap inside a group
+            } else if constexpr (MODE == kLegacyTabGlobal) {
+                ph = __ldg(tab + j + s);
+            } else if constexpr (MODE == kDirectPeriodic) {
+                uint32_t n = j + s + 1u;
+                if (n > p.period) n -= p.period;
+                ph = phasor(p.r, n);
+            } else {
+                ph = phasor(p.r, p.base + off + (uint32_t)(u * T * G + s));
+            }
+            res[s] = cmul_unfused(smp[u][s], ph);
+        }
+        store_group<OUT, G>(a.out, g0 + u * T, res);
+        if constexpr (MODE != kDirectLinear) {
+            j += p.step_u;
+            if (j >= p.period) j -= p.period;
+        }
+    }
+}
+
+// Generic per-sample tile: piece boundaries inside the tile and/or the ragged end of the buffer.
+template <int IN, int OUT, int T, int U>
+__device__ __noinline__ void slow_tile(const LegacyArgs& a, uint32_t pi, uint32_t k0)
+{
+    constexpr uint32_t kTile = tile_samples(IN, OUT, T, U);
+    DevPiece p = get_piece(a, pi);
+    for (uint32_t i = threadIdx.x; i < kTile; i += T) {
+        const uint32_t k = k0 + i;
+        if (k >= a.nsamples) break;
+        if (k >= p.k_end) {
+            pi = find_piece(a, pi, k);
+            p = get_piece(a, pi);
+        }
+        const uint32_t n = piece_samplenum(p, k - p.k_begin);
+        const float2 ph = phasor(p.r, n);
+        store_sample<OUT>(a.out, k, cmul_unfused(load_sample<IN>(a.in, k), ph));
+    }
+}
+
+// T threads per CTA, U groups per thread per tile, at least MINB resident CTAs per SM.
+template <int IN, int OUT, int T = kThreads, int U = kUnroll, int MINB = 0>
+__global__ void __launch_bounds__(T, MINB) mix_kernel(const __grid_constant__ LegacyArgs a)
+{
+    constexpr uint32_t kTile = tile_samples(IN, OUT, T, U);
+    extern __shared__ float2 tab_s[];
+
+    uint32_t tile, tile_end, tile_step;
+    if (a.interleave) {
+        tile = blockIdx.x;
+        tile_end = a.ntiles;
+        tile_step = gridDim.x;
+    } else {
+        tile = blockIdx.x * a.tiles_per_cta;
+        tile_end = min(tile + a.tiles_per_cta, a.ntiles);
+        tile_step = 1;
+    }
+    uint32_t pi = 0;
+    uint32_t staged = 0xffffffffu;   // piece whose table is in shared memory
+    DevPiece p = get_piece(a, 0);
+
+    for (; tile < tile_end; tile += tile_step) {
+        const uint32_t k0 = tile * kTile;
+        if (k0 >= p.k_end) {
+            pi = find_piece(a, pi, k0);
+            p = get_piece(a, pi);
+        }
+        const bool fast = (k0 + kTile <= p.k_end) && (k0 + kTile <= a.nsamples);
+        if (!fast) {
+            slow_tile<IN, OUT, T, U>(a, pi, k0);
+            continue;
+        }
+        if (p.period == 0) {
+            fast_tile<IN, OUT, kDirectLinear, T, U>(a, p, k0, nullptr);
+        } else if (p.tab == kNoTab) {
+            fast_tile<IN, OUT, kDirectPeriodic, T, U>(a, p, k0, nullptr);
+        } else if (p.period <= a.smem_entries) {
+            if (staged != pi) {            // CTA-uniform
+                __syncthreads();
+                for (uint32_t e = threadIdx.x; e < p.period + kTabPad; e += T)
+                    tab_s[e] = __ldg(a.tables + p.tab + e);
+                __syncthreads();
+                staged = pi;
+            }
+            fast_tile<IN, OUT, kLegacyTabShared, T, U>(a, p, k0, tab_s);
+        } else {
+            fast_tile<IN, OUT, kLegacyTabGlobal, T, U>(a, p, k0, a.tables + p.tab);
+        }
+    }
+}
+
+
+}  // namespace dmix
+
 using dmix::DevPiece;
 using dmix::MixArgs;
 
@@ -228,7 +393,7 @@ static void run_mix(uint64_t n, int interleave, int ctas_per_sm /*0 = occupancy*
     CK(cudaFuncGetAttributes(&fa, kern));
     constexpr int G = dmix::group_samples(IN, OUT);
     const uint32_t tile = dmix::tile_samples(IN, OUT, T, U);
-    MixArgs a;
+    dmix::LegacyArgs a;
     memset(&a, 0, sizeof a);
     a.in = g_buf.in;
     a.out = g_buf.out;
@@ -331,12 +496,12 @@ static void run_stream(uint64_t n, uint32_t period, float r, int tabmode /*0 sme
     a.tables = g_buf.tab;
     a.nsamples = (uint32_t)n;
     a.npieces = 1;
-    a.ntiles = (uint32_t)(n / C::kTileSamples);
+    const uint32_t ntiles = (uint32_t)(n / C::kTileSamples);
     a.nsegs = 1;
-    a.nunits = a.ntiles;
-    a.tail_begin = a.ntiles * C::kTileSamples;   // one GRID segment of whole tiles
+    a.nunits = ntiles;
+    a.tail_begin = ntiles * C::kTileSamples;   // one GRID segment of whole tiles
     a.inl_segs[0].unit_begin = 0;
-    a.inl_segs[0].unit_end = a.ntiles;
+    a.inl_segs[0].unit_end = ntiles;
     a.inl_segs[0].k_begin = 0;
     a.inl_segs[0].k_end = a.tail_begin;
     a.smem_piece = tabmode == 0 ? 0 : dmix::kNoPiece;
@@ -351,7 +516,7 @@ static void run_stream(uint64_t n, uint32_t period, float r, int tabmode /*0 sme
     magic_for(period, &d.magic, &d.shift);
     d.step_u = (uint32_t)C::kRow % period;
     a.inl[0] = d;
-    const uint32_t grid = std::min<uint32_t>((uint32_t)g_sms, (a.ntiles + WARPS - 1) / WARPS);
+    const uint32_t grid = std::min<uint32_t>((uint32_t)g_sms, (ntiles + WARPS - 1) / WARPS);
     Timing tm = time_it([&] { kern<<<grid, WARPS * 32, smem, g_stream>>>(a); });
     char extra[160];
     snprintf(extra, sizeof extra, ", \"regs\": %d, \"smem\": %d, \"inflight_kb_per_sm\": %d", fa.numRegs, (int)smem, WARPS * S * C::kTileIn / 1024);
