@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <numeric>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -154,6 +155,8 @@ struct KernShape {
 // segmented loop (GRID + COLUMN segments) with its own, larger tile.
 struct StreamShape {
     KernShape grid, seg;
+    KernShape direct;   // the lean loop with a larger tile, for launches whose samples are mostly in table-less pieces:
+                        // direct evaluation is issue-bound, so the per-tile pipeline overhead is what there is to save
 };
 
 // Longest period whose de-interleaved table (period + one row + padding entries of 8 bytes) still fits
@@ -184,11 +187,12 @@ using SegF32F32 = dmix::StreamCfg<1, 1, SEG_F32F32>;
 
 const StreamShape& shape_for(int in, int out)
 {
+    // direct shapes: profiles/r01_tune_direct_linear.jsonl
     static const StreamShape shapes[2][2] = {
-        {{make_shape<0, 0, 20, 2, 2, false>(), make_shape<0, 0, SEG_I16I16, true>()},
-         {make_shape<0, 1, 20, 3, 2, false>(), make_shape<0, 1, SEG_I16F32, true>()}},
-        {{make_shape<1, 0, 16, 2, 3, false>(), make_shape<1, 0, SEG_F32I16, true>()},
-         {make_shape<1, 1, 16, 2, 2, false>(), make_shape<1, 1, SEG_F32F32, true>()}},
+        {{make_shape<0, 0, 20, 2, 2, false>(), make_shape<0, 0, SEG_I16I16, true>(), make_shape<0, 0, 12, 2, 6, false>()},
+         {make_shape<0, 1, 20, 3, 2, false>(), make_shape<0, 1, SEG_I16F32, true>(), make_shape<0, 1, 16, 2, 4, false>()}},
+        {{make_shape<1, 0, 16, 2, 3, false>(), make_shape<1, 0, SEG_F32I16, true>(), make_shape<1, 0, 16, 2, 6, false>()},
+         {make_shape<1, 1, 16, 2, 2, false>(), make_shape<1, 1, SEG_F32F32, true>(), make_shape<1, 1, 16, 2, 2, false>()}},
     };
     return shapes[in][out];
 }
@@ -439,7 +443,7 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
     const StreamShape& shapes = shape_for(intype, outtype);
     const size_t ibps = bytes_per_sample(intype), obps = bytes_per_sample(outtype);
     // launches are cut at a common multiple of both kernels' tiles so that every launch but the last has no ragged tail
-    const uint64_t lcm_tile = (uint64_t)shapes.grid.tile_samples * shapes.seg.tile_samples;
+    const uint64_t lcm_tile = std::lcm<uint64_t>(std::lcm<uint64_t>(shapes.grid.tile_samples, shapes.seg.tile_samples), shapes.direct.tile_samples);
     const uint64_t launch_max = kLaunchMaxSamples / lcm_tile * lcm_tile;
 
     if (ctx->tables_event_valid) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->tables_ready, 0));
@@ -474,7 +478,9 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
                                                    (uint32_t)ctx->sm_count * (uint32_t)shapes.seg.warps, &segs);
         // no COLUMN segment: the whole launch is one GRID segment and takes the lean loop
         const bool grid_only = segs.size() <= 1 && (segs.empty() || segs[0].rows == 0);
-        const KernShape& shape = grid_only ? shapes.grid : shapes.seg;
+        uint64_t tableless = 0;
+        for (size_t i = 0; i < dev.size(); i++) tableless += dev[i].tab == dmix::kNoTab ? dev_len[i] : 0;
+        const KernShape& shape = !grid_only ? shapes.seg : 2 * tableless > nsamp ? shapes.direct : shapes.grid;
         // one table per launch is staged in shared memory: the eligible piece covering most samples
         uint32_t smem_piece = dmix::kNoPiece;
         uint64_t smem_piece_len = 0;
@@ -719,7 +725,7 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     for (int i = 0; i < 2 && e2 == cudaSuccess; i++)
         for (int o = 0; o < 2 && e2 == cudaSuccess; o++) {
             const StreamShape& sh = shape_for(i, o);
-            for (const KernShape* k : {&sh.grid, &sh.seg})
+            for (const KernShape* k : {&sh.grid, &sh.seg, &sh.direct})
                 if (e2 == cudaSuccess)
                     e2 = cudaFuncSetAttribute(k->kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)(k->fixed_smem + k->table_bytes(k->smem_tab_entries)));

@@ -513,8 +513,10 @@ static void run_stream(uint64_t n, uint32_t period, float r, int tabmode /*0 sme
     d.period = period;
     d.r = r;
     d.tab = tabmode == 2 ? dmix::kNoTab : 0;
-    magic_for(period, &d.magic, &d.shift);
-    d.step_u = (uint32_t)C::kRow % period;
+    if (period) {
+        magic_for(period, &d.magic, &d.shift);
+        d.step_u = (uint32_t)C::kRow % period;
+    }
     a.inl[0] = d;
     const uint32_t grid = std::min<uint32_t>((uint32_t)g_sms, (ntiles + WARPS - 1) / WARPS);
     Timing tm = time_it([&] { kern<<<grid, WARPS * 32, smem, g_stream>>>(a); });
@@ -547,6 +549,22 @@ static void sweep_stream(uint64_t n)
     sweep_stream_w<IN, OUT, 24>(n);
     sweep_stream_w<IN, OUT, 28>(n);
     sweep_stream_w<IN, OUT, 32>(n);
+}
+
+// direct (table-free) evaluation on a piece that never resets, r = 1 Hz / 2 Gsps: per-tile pipeline overhead
+// against tile size, lean loop
+template <int IN, int OUT>
+static void sweep_direct(uint64_t n)
+{
+    const float r = 1.0f / 2.0e9f;
+    run_stream<IN, OUT, 20, 2, 2>(n, 0, r, 2);
+    run_stream<IN, OUT, 16, 2, 3>(n, 0, r, 2);
+    run_stream<IN, OUT, 16, 2, 4>(n, 0, r, 2);
+    run_stream<IN, OUT, 12, 2, 4>(n, 0, r, 2);
+    run_stream<IN, OUT, 12, 2, 6>(n, 0, r, 2);
+    run_stream<IN, OUT, 16, 2, 6>(n, 0, r, 2);
+    run_stream<IN, OUT, 8, 2, 8>(n, 0, r, 2);
+    run_stream<IN, OUT, 12, 2, 8>(n, 0, r, 2);
 }
 
 template <int IN, int OUT>
@@ -604,6 +622,8 @@ int main(int argc, char** argv)
             sweep_pair<0, 1>(n_small);
             sweep_stream<0, 0>(n_small);
             sweep_stream<0, 1>(n_small);
+            sweep_direct<0, 0>(n_small);
+            sweep_direct<0, 1>(n_small);
             if (big) {
                 run_mix<0, 0, 256, 4, 0>(n_big, 0, 0, 256, -15000.0f / 256000.0f);
                 run_mix<0, 0, 256, 4, 0>(n_big, 1, 0, 256, -15000.0f / 256000.0f);
@@ -614,6 +634,8 @@ int main(int argc, char** argv)
             sweep_pair<1, 1>(n_small);
             sweep_stream<1, 0>(n_small);
             sweep_stream<1, 1>(n_small);
+            sweep_direct<1, 0>(n_small);
+            sweep_direct<1, 1>(n_small);
             if (big) {
                 run_mix<1, 0, 256, 4, 0>(n_big, 0, 0, 256, -15000.0f / 256000.0f);
                 run_mix<1, 0, 256, 4, 0>(n_big, 1, 0, 256, -15000.0f / 256000.0f);
