@@ -89,7 +89,7 @@ def test_cfg3_track_replay_i16_full_size(oracle, mixer):
     x = torch.empty(n * 4, dtype=torch.uint8, device="cuda")
     y = torch.empty(n * 4, dtype=torch.uint8, device="cuda")
     _fill(x, I16)
-    _, _, _, stats = dsp.plan_tiles_trace(I16, I16, 0, shifts[:4 * fs // bs], bs, fs, 4 * fs)
+    _, _, _, stats = dsp.plan_tiles_trace(I16, I16, 0, shifts[:8 * fs // bs], bs, fs, 8 * fs)
     assert stats["column_segments"] >= 2, stats        # long-period pieces do take the COLUMN path
     sn = mixer.mix_blocks_dev(x.data_ptr(), x.numel(), I16, I16, shifts, fs, 0, y.data_ptr(), y.numel())
     mixer.synchronize()

@@ -256,12 +256,12 @@ def test_direct_fast_rows_match_oracle(oracle, mixer, shift, fs, sn0, n):
 
 # Periods above the shared-memory table size with several whole periods in the launch: COLUMN segments
 # (phasors of a column evaluated once, parked in shared memory, reused over rows; mixer_kernels.cuh).
-COLUMN_CASES = [
-    (-9876.54, 1_024_000, 0, 2_500_003),            # P = 111 145 (odd): rows at every alignment shift
-    (7321.7, 1_024_000, 17, 1_300_001),             # P = 55 244, starts mid-period
-    (-3_912_345.25, 200_000_000, 0, 700_000),       # P = 26 787
-    (12_345.678, 1_024_000, 0, 1_000_000),
-    (-1234.5, 96_000, 3, 900_002),
+COLUMN_CASES = [   # launches of at least 4 Mi samples (smaller ones are latency-bound and stay on the GRID path)
+    (-9876.54, 1_024_000, 0, 5_500_003),            # P = 111 145 (odd): rows at every alignment shift
+    (7321.7, 1_024_000, 17, 4_300_001),             # P = 55 244, starts mid-period
+    (-3_912_345.25, 200_000_000, 0, 4_700_000),     # P = 26 787
+    (12_345.678, 1_024_000, 0, 4_200_000),
+    (-1234.5, 96_000, 3, 4_900_002),
 ]
 
 
@@ -295,7 +295,7 @@ def test_column_segments_in_a_track_schedule(oracle, mixer):
     for intype, outtype in TYPE_PAIRS:
         nbytes = shifts.size * BUFFER_SIZE - BPS[intype] * 777
         if intype == F32:
-            nbytes = shifts.size * BUFFER_SIZE // 2   # f32 blocks hold half as many samples: 2.5 s of stream
+            nbytes = shifts.size * BUFFER_SIZE - 8 * 333   # f32 blocks hold half as many samples: 2.5 s of stream (GRID path)
         buf = make_input(rng, nbytes // BPS[intype], intype)
         got, sn = mixer.mix_blocks(buf, intype, outtype, shifts, fs)
         want, sn_ref = oracle.mix_blocks(buf, intype, outtype, shifts, fs)
@@ -312,7 +312,7 @@ def test_random_schedules_all_type_pairs(oracle, mixer):
         intype, outtype = TYPE_PAIRS[trial % 4]
         fs = int(rng.choice([96_000, 1_024_000, 2_400_000]))
         nruns = int(rng.integers(1, 6))
-        shifts = np.concatenate([np.repeat(rng.choice(pool), int(rng.integers(1, 400))) for _ in range(nruns)])
+        shifts = np.concatenate([np.repeat(rng.choice(pool), int(rng.integers(1, 1400))) for _ in range(nruns)])   # up to ~14 M samples
         nbytes = shifts.size * BUFFER_SIZE - BPS[intype] * int(rng.integers(0, BUFFER_SIZE // BPS[intype]))
         start = int(rng.choice([0, 1, 77_777, 2**24 + 5, 2**32 - 3]))
         buf = make_input(rng, nbytes // BPS[intype], intype)

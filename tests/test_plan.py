@@ -117,9 +117,10 @@ def test_replay_schedule_matches_reference_clock(oracle, intype, fs):
 # ---- work decomposition of one kernel launch (GRID / COLUMN segments, mixer_kernels.cuh) -------------
 TILE_CASES = [
     # (shift, fs, start samplenum, samples): periods above the shared-memory table size become COLUMN segments
-    (-9876.54, 1_024_000, 0, 3_000_001),          # P = 111 145 (odd): every row has a different alignment shift
-    (7321.7, 1_024_000, 0, 1_024_003),            # P = 55 244
-    (-3_912_345.25, 200_000_000, 12_345, 500_000),  # P = 26 787, starts mid-period
+    (-9876.54, 1_024_000, 0, 5_000_001),          # P = 111 145 (odd): every row has a different alignment shift
+    (7321.7, 1_024_000, 0, 4_224_003),            # P = 55 244
+    (-3_912_345.25, 200_000_000, 12_345, 4_500_000),  # P = 26 787, starts mid-period
+    (7321.7, 1_024_000, 0, 1_024_003),            # below the COLUMN launch threshold: GRID tiles, direct evaluation
     (4_000_000.5, 200_000_000, 0, 400_000),       # P = 4.9 M > samples: linear piece only, GRID
     (-15000.0, 256000, 7, 100_003),               # P = 256: table piece, GRID only
     (5000.0, 1_024_000, 0, 300_000),              # P = 1024
@@ -139,6 +140,8 @@ def test_launch_tiles_cover_every_sample_once_with_the_reference_samplenum(oracl
         assert count - tail < 4
         assert np.all(cover[:tail] == 1) and np.all(cover[tail:] == 0), stats
         assert np.array_equal(trace[:tail], want[:tail]), stats
+        if count >= 4 << 20 and abs(shift) in (9876.54, 7321.7, 3_912_345.25):
+            assert stats["column_segments"] == 1, stats   # long period, several periods, large launch: the COLUMN path
 
 
 def test_launch_tiles_track_schedule(oracle):
