@@ -340,3 +340,18 @@ def test_host_path_multi_chunk_with_long_periods(oracle, mixer):
     want, sn_ref = oracle.mix_blocks(buf[:nbytes], I16, F32, shifts, 1_024_000)
     assert sn == sn_ref
     check(oracle, got, want, F32)
+
+
+@pytest.mark.parametrize("shift,fs", [(float("inf"), 48000), (float("-inf"), 48000), (float("nan"), 48000), (1000.0, 0), (0.0, 0),
+                                      (3.0e38, 1), (1.0e-30, 4_000_000_000)])
+def test_degenerate_ratios(oracle, mixer, shift, fs):
+    """r = shift / fs that is Inf, NaN (x / 0, Inf / fs), huge or denormal-small: the reference just runs its f32
+    arithmetic (NaN phasors -> NaN f32 output, 0 after the saturating i16 cast); so must the kernels."""
+    rng = np.random.default_rng(3)
+    for intype, outtype in TYPE_PAIRS:
+        for n in (5, 70_001):
+            buf = make_input(rng, n, intype)
+            got, sn = mixer.mix(buf, intype, outtype, shift, fs)
+            want, sn_ref = oracle.mix(buf, intype, outtype, shift, fs)
+            assert sn == sn_ref
+            check(oracle, got, want, outtype)

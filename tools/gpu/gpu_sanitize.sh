@@ -14,8 +14,11 @@ m = doppler_b200.Mixer(0)
 rng = np.random.default_rng(5)
 bad = 0
 for it, ot in [(I16, I16), (I16, F32), (F32, I16), (F32, F32)]:
-    for shift, fs, n in [(-15000.0, 256000, 70_001), (-3_912_345.25, 200_000_000, 200_003), (7321.7, 1_024_000, 130_001),
-                         (1.0, 2_000_000_000, 50_001)]:
+    cases = [(-15000.0, 256000, 70_001), (-3_912_345.25, 200_000_000, 200_003), (7321.7, 1_024_000, 130_001),
+             (1.0, 2_000_000_000, 50_001)]
+    if it == ot:
+        cases.append((-9876.54, 1_024_000, 4_300_003))   # >= 4 Mi samples, long period: COLUMN segments, dynamic unit claiming
+    for shift, fs, n in cases:
         if it == I16:
             buf = rng.integers(-32768, 32768, 2 * n, dtype=np.int32).astype(np.int16).view(np.uint8)
         else:
@@ -33,22 +36,3 @@ for tool in memcheck racecheck synccheck; do
   timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py > $OUT/san_$tool.log 2>&1; echo "rc=$?"
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|Invalid|MISMATCH" $OUT/san_$tool.log | head -12
 done
-echo "== cli timing"
-BIN=doppler_b200/bin/doppler
-python - <<PY
-import numpy as np
-rng = np.random.default_rng(1)
-rng.integers(-20000, 20000, 2048 * 1024 * 1024, dtype=np.int16).tofile("/dev/shm/iq4g.bin")   # 4 GiB = 1 Gi samples
-PY
-s=$(date +%s.%N); $BIN const -s 2000000000 -i i16 --shift -117187500 < /dev/null > /dev/null 2>&1; e=$(date +%s.%N)
-python -c "print('{\"cli\": \"empty input (start-up)\", \"seconds\": %.3f}' % ($e-$s))" | tee $OUT/cli2.jsonl
-for mode in pipe file; do
-  for rep in 1 2; do
-    s=$(date +%s.%N)
-    if [ $mode = pipe ]; then cat /dev/shm/iq4g.bin | $BIN const -s 2000000000 -i i16 --shift -117187500 2>/dev/null | cat > /dev/null
-    else $BIN const -s 2000000000 -i i16 --shift -117187500 < /dev/shm/iq4g.bin > /dev/null 2>/dev/null; fi
-    e=$(date +%s.%N)
-    python -c "n=1073741824; t=$e-$s; print('{\"cli\": \"const i16->i16 4 GiB, stdin=$mode\", \"seconds\": %.3f, \"msps\": %.1f, \"in_MBps\": %.0f}' % (t, n/t/1e6, n*4/t/1e6))" | tee -a $OUT/cli2.jsonl
-  done
-done
-rm -f /dev/shm/iq4g.bin
