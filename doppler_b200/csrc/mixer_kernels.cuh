@@ -256,7 +256,7 @@ enum FastMode { kTabShared = 0, kTabGlobal = 1 };   // phasor table staged in sh
 // =============================================================================================
 // Streaming kernel: every warp is an independent bulk-async (TMA 1-D) pipeline.
 //
-// Measured on B200 (profiles/r01_tune_*.md): a register-staged LDG/STG loop tops out at
+// Measured on B200 (profiles/r01_tune_*.jsonl): a register-staged LDG/STG loop tops out at
 // 0.85-0.93 of the measured copy peak however it is shaped, while cp.async.bulk pipelines reach
 // 0.99-1.02 when -- and only when -- about 32-48 KB of loads are in flight per SM (more in
 // flight is *slower*: 0.93-0.95).  So the mixer moves its tiles with cp.async.bulk: global ->
