@@ -182,8 +182,19 @@ def run_reference(args):
         "data": "synthetic", "config": workload_config(args.gpus), "cpu_baseline": base,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line, on the process's real stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -196,6 +207,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything libraries print there meanwhile (NCCL's version banner,
+    # torchrun children ...) is sent to stderr by pointing fd 1 at fd 2 until the line is ready
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(3, args.warmup)
@@ -212,9 +229,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -358,7 +373,7 @@ def main():
             "data": "synthetic", "config": workload_config(world), "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     mixer.close()
     if world > 1:
         dist.destroy_process_group()
