@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -616,11 +617,33 @@ bool is_pinned(const void* p)
     return at.type == cudaMemoryTypeHost;
 }
 
+// Staging copies between the caller's pageable buffers and the pinned slots: a single thread moves ~10 GB/s,
+// a fifth of what PCIe takes, so large copies are split over a few threads (measured 0.9 -> see
+// profiles/r01_percall_latency.jsonl).  Callers with pinned buffers (doppler_b200_host_alloc / _register) skip this.
+void staged_copy(void* dst, const void* src, size_t bytes)
+{
+    constexpr size_t kPerThread = 4u << 20;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nthreads = std::min<size_t>({bytes / kPerThread, (size_t)(hw ? hw : 1), (size_t)4});
+    if (nthreads <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t part = (bytes / nthreads + 63) & ~(size_t)63;
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nthreads; t++) {
+        const size_t off = t * part, len = off >= bytes ? 0 : std::min(part, bytes - off);
+        if (len) th.emplace_back([=] { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+    }
+    memcpy(dst, src, std::min(part, bytes));
+    for (std::thread& x : th) x.join();
+}
+
 int retire_slot(doppler_b200_ctx* ctx, Slot& sl)
 {
     if (!sl.busy) return DOPPLER_B200_OK;
     CUDA_TRY(ctx, cudaEventSynchronize(sl.done));
-    if (sl.user_out) memcpy(sl.user_out, sl.h_out, sl.user_out_bytes);
+    if (sl.user_out) staged_copy(sl.user_out, sl.h_out, sl.user_out_bytes);
     sl.user_out = nullptr;
     sl.busy = false;
     return DOPPLER_B200_OK;
@@ -648,7 +671,7 @@ int mix_host(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int intyp
         if (rc) return rc;
         const char* src = static_cast<const char*>(in) + k * ibps;
         if (!in_pinned) {
-            memcpy(sl.h_in, src, n * ibps);
+            staged_copy(sl.h_in, src, n * ibps);
             src = static_cast<const char*>(sl.h_in);
         }
         CUDA_TRY(ctx, cudaMemcpyAsync(sl.d_in, src, n * ibps, cudaMemcpyHostToDevice, sl.stream));
