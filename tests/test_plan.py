@@ -182,3 +182,23 @@ def test_launch_tiles_random_schedules(oracle):
         assert count - tail < 4, (trial, stats)
         assert np.all(cover[:tail] == 1) and np.all(cover[tail:] == 0), (trial, stats)
         assert np.array_equal(trace[:tail], want[:tail]), (trial, stats)
+
+
+def test_trace_property_random_ratios(oracle):
+    """Property: for ANY (shift, samplerate, start state) the planner's closed-form pieces expand to the
+    reference recurrence (dsp.rs:125-130) sample for sample, and the carried state matches."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(shift=st.one_of(st.integers(-2_000_000, 2_000_000).map(float), st.floats(-1e6, 1e6, allow_nan=False, width=32)),
+           fs=st.sampled_from([8000, 48000, 96000, 256000, 1_024_000, 2_400_000, 10_000_000, 200_000_000]),
+           start=st.one_of(st.integers(0, 300_000), st.integers(2**24 - 5, 2**24 + 5), st.integers(2**32 - 20_000, 2**32 - 1)),
+           count=st.integers(1, 40_000))
+    def prop(shift, fs, start, count):
+        want, sn_want = oracle.samplenum_trace(start, shift, fs, count)
+        got, sn, _ = dsp.plan_trace(start, [shift], count, fs, count)
+        assert np.array_equal(got, want)
+        assert sn == sn_want
+        assert dsp.samplenum_advance(start, shift, fs, count) == sn_want
+
+    prop()
