@@ -76,6 +76,7 @@ struct TableRef {
 };
 
 struct MetaSlot {
+    cudaEvent_t copied = nullptr;   // the image has reached the device (recorded on the context's copy stream)
     void* host = nullptr;   // pinned staging image
     void* dev = nullptr;    // its device copy (persistent: stream-ordered pool memory is trimmed at every synchronize)
     size_t cap = 0;
@@ -112,6 +113,7 @@ struct doppler_b200_ctx {
     Slot slots[kSlots];
     MetaSlot meta[kMetaSlots];   // pinned staging for launch metadata (pieces, segments, work-unit counter)
     uint32_t meta_next = 0;
+    cudaStream_t meta_stream = nullptr;   // metadata uploads run here, beside the previous launch's kernel
     std::string err;
     uint64_t launches = 0;
 };
@@ -536,14 +538,21 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
                 CUDA_TRY(ctx, cudaMalloc(&ms.dev, cap));
                 ms.cap = cap;
             }
-            if (!ms.done) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ms.done, cudaEventDisableTiming));
+            if (!ms.done) {
+                CUDA_TRY(ctx, cudaEventCreateWithFlags(&ms.done, cudaEventDisableTiming));
+                CUDA_TRY(ctx, cudaEventCreateWithFlags(&ms.copied, cudaEventDisableTiming));
+            }
             char* h = static_cast<char*>(ms.host);
             memset(h, 0, 16);   // the work-unit counter starts at 0
             if (up_pieces) memcpy(h + off_pieces, dev.data(), dev.size() * sizeof(DevPiece));
             if (up_segs) memcpy(h + off_segs, segs.data(), segs.size() * sizeof(DevSeg));
             if (!index.empty()) memcpy(h + off_index, index.data(), index.size() * sizeof(uint32_t));
             d_meta = static_cast<char*>(ms.dev);
-            CUDA_TRY(ctx, cudaMemcpyAsync(d_meta, h, bytes, cudaMemcpyHostToDevice, s));
+            // on the context's own copy stream: the upload overlaps whatever the caller's stream is still running
+            // (the previous launch, when calls are queued back to back); the kernel waits for it through an event
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_meta, h, bytes, cudaMemcpyHostToDevice, ctx->meta_stream));
+            CUDA_TRY(ctx, cudaEventRecord(ms.copied, ctx->meta_stream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(s, ms.copied, 0));
             meta_slot = &ms;
             a.unit_counter = reinterpret_cast<uint32_t*>(d_meta);
             if (up_pieces) a.pieces = reinterpret_cast<const DevPiece*>(d_meta + off_pieces);
@@ -746,6 +755,7 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&ctx->meta_stream, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->tables_ready, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e2 == cudaSuccess; i++)
         for (int o = 0; o < 2 && e2 == cudaSuccess; o++) {
@@ -778,7 +788,9 @@ void doppler_b200_destroy(doppler_b200_ctx* ctx)
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->meta_stream) cudaStreamDestroy(ctx->meta_stream);
     for (MetaSlot& ms : ctx->meta) {
+        if (ms.copied) cudaEventDestroy(ms.copied);
         if (ms.host) cudaFreeHost(ms.host);
         if (ms.dev) cudaFree(ms.dev);
         if (ms.done) cudaEventDestroy(ms.done);
