@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -666,7 +667,13 @@ int mix_host(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int intyp
 {
     const size_t ibps = bytes_per_sample(intype), obps = bytes_per_sample(outtype);
     // chunk = whole number of shift blocks and of the largest tile
-    uint64_t chunk = kHostChunkBytes / ibps;
+    // DOPPLER_B200_CHUNK_MB: tuning knob for the pipeline chunk (tools/tune); the default was chosen on B200
+    static const size_t chunk_bytes = [] {
+        const char* e = getenv("DOPPLER_B200_CHUNK_MB");
+        const long mb = e ? atol(e) : 0;
+        return mb >= 1 && mb <= 1024 ? (size_t)mb << 20 : kHostChunkBytes;
+    }();
+    uint64_t chunk = chunk_bytes / ibps;
     if (block_samples && nblocks > 1) chunk = std::max<uint64_t>(block_samples, chunk / block_samples * block_samples);
     const bool in_pinned = is_pinned(in), out_pinned = is_pinned(out);
     uint32_t sn = *samplenum;

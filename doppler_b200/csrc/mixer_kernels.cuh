@@ -643,7 +643,7 @@ __device__ __forceinline__ void stream_tile_column(const uint32_t (&raw)[C::U][4
 }
 
 // Lane 0's work iterator: expands work units into tiles.  On the device, units are claimed
-// kUnitChunk at a time from a global counter (a COLUMN unit costs 2-16 tiles plus a window evaluation,
+// kUnitChunk at a time from a global counter (a COLUMN unit costs 2-64 tiles plus a window evaluation,
 // a GRID unit kGridUnitTiles tiles: a static split left ~10 % of the SMs idle at the end of a track-mode launch);
 // the claim for the NEXT chunk is issued when a chunk starts, so its latency hides behind the
 // chunk's tiles.  On the host (doppler_b200_plan_tiles_trace) pipeline p walks chunks p, p + npipes, ...
