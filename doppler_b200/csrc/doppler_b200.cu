@@ -179,9 +179,10 @@ template <int IN, int OUT, int WARPS, int S, int U, bool SEG>
 KernShape make_shape()
 {
     using C = dmix::StreamCfg<IN, OUT, WARPS, S, U>;
+    constexpr uint32_t fixed = SEG ? (uint32_t)C::kFixedSmem : (uint32_t)C::kGridSmem;
     return KernShape{SEG ? dmix::mix_stream_kernel<IN, OUT, WARPS, S, U> : dmix::mix_grid_kernel<IN, OUT, WARPS, S, U>, WARPS,
-                     (uint32_t)C::kTileSamples, (uint32_t)C::kRow, (uint32_t)C::kGran, (uint32_t)C::kFixedSmem, &C::table_bytes,
-                     smem_tab_capacity((uint32_t)C::kFixedSmem, (uint32_t)C::kRow)};
+                     (uint32_t)C::kTileSamples, (uint32_t)C::kRow, (uint32_t)C::kGran, fixed, &C::table_bytes,
+                     smem_tab_capacity(fixed, (uint32_t)C::kRow)};
 }
 
 // (WARPS, S, U) of the segmented kernel per type pair; the host walk of the work decomposition
@@ -193,6 +194,9 @@ using SegF32F32 = dmix::StreamCfg<1, 1, SEG_F32F32>;
 
 const StreamShape& shape_for(int in, int out)
 {
+    // lean (grid) shapes: chosen under SUSTAINED load -- launches queued back to back pull the SM clock to ~1.65 GHz
+    // under the 1 kW power cap, which favours fewer, larger tiles over more warps (profiles/r01_tune_sustained.jsonl;
+    // isolated launches prefer (24,2,2) for f32->i16, r01_tune_stream_smemtab_fmul2.jsonl).
     // direct shapes: profiles/r01_tune_direct_linear.jsonl
     static const StreamShape shapes[2][2] = {
         {{make_shape<0, 0, 20, 2, 2, false>(), make_shape<0, 0, SEG_I16I16, true>(), make_shape<0, 0, 12, 2, 6, false>()},

@@ -336,7 +336,8 @@ struct StreamCfg {
     static constexpr int kWinIters = (kTileSamples + kWinLead + 1 + 31) / 32;
     static constexpr int kWinPlane = ((32 * kWinIters / G + 15) / 16) * 16 + 16 / G;
     static constexpr int kWinBytes = G * kWinPlane * 8;            // per warp
-    static constexpr int kFixedSmem = kBarBytes + WARPS * (kRing + kDescBytes + kWinBytes);
+    static constexpr int kFixedSmem = kBarBytes + WARPS * (kRing + kDescBytes + kWinBytes);   // mix_stream_kernel
+    static constexpr int kGridSmem = kBarBytes + WARPS * kRing;                                // mix_grid_kernel (no descriptors / windows)
     // shared-memory table: G planes of plane_len(entries) float2 each
     __host__ __device__ static constexpr uint32_t plane_len(uint32_t period) { return (period + kRow + G - 1) / G + 1; }
     __host__ __device__ static constexpr uint32_t table_bytes(uint32_t period) { return G * plane_len(period) * 8; }
@@ -912,7 +913,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_grid_kernel(const __grid_co
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     unsigned char* rings = smem + C::kBarBytes;
-    float2* tab_s = reinterpret_cast<float2*>(smem + C::kFixedSmem);
+    float2* tab_s = reinterpret_cast<float2*>(smem + C::kGridSmem);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t* full = bars + warp * S;

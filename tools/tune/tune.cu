@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -323,6 +324,29 @@ static Timing time_it(F&& launch, int iters = 15)
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     std::vector<double> t;
+    if (getenv("TUNE_SUSTAINED")) {
+        // bench.py's regime: launches queued back to back under load (the 1 kW power cap pulls the SM clock to
+        // ~1.65 GHz after a few hundred ms of streaming) -- 0.4 s of warm-up launches, then batches of 10
+        auto t0 = std::chrono::steady_clock::now();
+        while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < 0.4) {
+            for (int i = 0; i < 20; i++) launch();
+            CK(cudaStreamSynchronize(g_stream));
+        }
+        for (int rep = 0; rep < 5; rep++) {
+            CK(cudaEventRecord(e0, g_stream));
+            for (int i = 0; i < 10; i++) launch();
+            CK(cudaEventRecord(e1, g_stream));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaGetLastError());
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            t.push_back(ms * 1e3 / 10);
+        }
+        std::sort(t.begin(), t.end());
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return Timing{t[t.size() / 2], t[0]};
+    }
     for (int i = 0; i < 3 + iters; i++) {
         CK(cudaEventRecord(e0, g_stream));
         launch();
@@ -484,7 +508,7 @@ static void run_stream(uint64_t n, uint32_t period, float r, int tabmode /*0 sme
              tabmode == 0 ? "smemtab" : tabmode == 1 ? "l2tab" : "direct", period);
     if (!want(name)) return;
     auto kern = dmix::mix_grid_kernel<IN, OUT, WARPS, S, U>;
-    const size_t smem = C::kFixedSmem + (tabmode == 0 ? C::table_bytes(period) : 0);
+    const size_t smem = C::kGridSmem + (tabmode == 0 ? C::table_bytes(period) : 0);
     if (smem > 227 * 1024) return;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa;
