@@ -180,8 +180,12 @@ KernShape make_shape()
 {
     using C = dmix::StreamCfg<IN, OUT, WARPS, S, U>;
     constexpr uint32_t fixed = SEG ? (uint32_t)C::kFixedSmem : (uint32_t)C::kGridSmem;
-    return KernShape{SEG ? dmix::mix_stream_kernel<IN, OUT, WARPS, S, U> : dmix::mix_grid_kernel<IN, OUT, WARPS, S, U>, WARPS,
-                     (uint32_t)C::kTileSamples, (uint32_t)C::kRow, (uint32_t)C::kGran, fixed, &C::table_bytes,
+    MixKernel kern;
+    if constexpr (SEG)   // only the kernel this shape is for gets instantiated
+        kern = dmix::mix_stream_kernel<IN, OUT, WARPS, S, U>;
+    else
+        kern = dmix::mix_grid_kernel<IN, OUT, WARPS, S, U>;
+    return KernShape{kern, WARPS, (uint32_t)C::kTileSamples, (uint32_t)C::kRow, (uint32_t)C::kGran, fixed, &C::table_bytes,
                      smem_tab_capacity(fixed, (uint32_t)C::kRow)};
 }
 
