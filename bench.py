@@ -169,6 +169,8 @@ def run_reference(args):
     base = None
     steps = max(1, args.steps)
     per_step = max(1.0, min(12.0, 150.0 / (steps + args.warmup)))
+    if os.environ.get("DOPPLER_BENCH_CPU_SECONDS"):   # tests/test_bench_contract.py: a short sample
+        per_step = float(os.environ["DOPPLER_BENCH_CPU_SECONDS"])
     for i in range(args.warmup + steps):
         base, n, t = cpu_baseline(threads, seconds_target=per_step)
         if i >= args.warmup:
