@@ -175,7 +175,6 @@ uint64_t Planner::hit_distance(float r, uint32_t n, uint64_t count)
         if (it->second.found) return it->second.dist < count ? it->second.dist : count;
         if (it->second.dist >= count) return count;   // dist = samples known to be hit-free
     }
-    if (hits_.size() > (1u << 16)) hits_.clear();
     const uint64_t done = it != hits_.end() ? it->second.dist : 0;
     const uint64_t d = done + first_hit(r, n + (uint32_t)done, count - done);
     hits_[key] = HitInfo{d < count ? d : count, d < count};
@@ -184,6 +183,10 @@ uint64_t Planner::hit_distance(float r, uint32_t n, uint64_t count)
 
 void Planner::plan(const std::vector<Run>& runs, uint64_t k0, uint32_t* samplenum, std::vector<Piece>* out)
 {
+    // Realtime track mode forms a new ratio for every 8192-byte block, for hours: keep the per-ratio caches
+    // bounded (trimmed here, where no reference into them is live).
+    if (cache_.size() > (1u << 16)) cache_.clear();
+    if (hits_.size() > (1u << 16)) hits_.clear();
     uint32_t n = *samplenum;
     uint64_t k = k0;
     for (const Run& run : runs) {
