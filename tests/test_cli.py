@@ -218,3 +218,29 @@ def test_live_pipe_latency_and_trickled_input(oracle):
         got += chunk
     assert p.wait(timeout=30) == 0
     assert bytes(got) == want.tobytes()
+
+
+@pytest.mark.gpu
+def test_track_realtime_mode_shifts_without_changing_magnitudes(tmp_path):
+    """`doppler track` without --time (main.rs:186-206): Doppler at the wall clock, block by block.  The shift is
+    not reproducible, but a frequency shift never changes |z|: every output magnitude equals the input's within the
+    i16 truncation, and the stream length is kept."""
+    f = tmp_path / "cubesat.txt"
+    f.write_text("SYNTHETIC TEST SAT\n" + L1 + "\n" + L2 + "\n")
+    fs = 256000
+    n = 2048 * 20 + 55
+    t = np.arange(n)
+    sig = 0.25 * np.exp(2j * np.pi * 15000.0 / fs * t)
+    iq = np.empty(2 * n, dtype="<i2")
+    iq[0::2] = np.round(sig.real * 32767)
+    iq[1::2] = np.round(sig.imag * 32767)
+    r = run(["track", "-s", str(fs), "-i", "i16", "--tlefile", str(f), "--tlename", "SYNTHETIC TEST SAT", "--location",
+             "lat=58.26541,lon=26.46667,alt=76", "--frequency", "437505000"], iq.tobytes())
+    assert r.returncode == 0, r.stderr
+    out = np.frombuffer(r.stdout, dtype="<i2").astype(np.float64)
+    assert out.size == iq.size
+    mag_in = np.hypot(iq[0::2].astype(np.float64), iq[1::2].astype(np.float64))
+    mag_out = np.hypot(out[0::2], out[1::2])
+    assert np.abs(mag_out - mag_in).max() < 3.0
+    assert not np.array_equal(out, iq.astype(np.float64))   # it did shift
+    # (the telemetry of main.rs:191-199 only appears once a second of wall time has passed)
