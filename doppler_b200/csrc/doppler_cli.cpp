@@ -524,6 +524,11 @@ int main(int argc, char** argv)
             const double doppler_hz = doppler_b200_doppler_hz(ob.range_rate_km_s, args.frequency);
             if (time(nullptr) - last_log >= 1) {   // main.rs:191-199
                 last_log = time(nullptr);
+                char ts[40];
+                struct tm gm;
+                gmtime_r(&last_log, &gm);
+                strftime(ts, sizeof ts, "%Y-%m-%dT%H:%M:%SZ", &gm);   // time::now_utc().rfc3339()
+                INFO("time                : %s", ts);
                 INFO("az                  : %.2f\xC2\xB0", ob.az_deg);
                 INFO("el                  : %.2f\xC2\xB0", ob.el_deg);
                 INFO("range               : %.0f km", ob.range_km);
