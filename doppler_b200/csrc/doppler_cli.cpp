@@ -607,6 +607,12 @@ int main(int argc, char** argv)
                     doppler_hz = doppler_b200_doppler_hz(ob.range_rate_km_s, args.frequency);
                     if (sec - last_logged_second >= 5) {   // main.rs:167-175
                         last_logged_second = sec;
+                        char ts[40];
+                        struct tm gm;
+                        const time_t tt = (time_t)(args.start_unix + sec);
+                        gmtime_r(&tt, &gm);
+                        strftime(ts, sizeof ts, "%Y-%m-%dT%H:%M:%SZ", &gm);   // (start_time + dt).to_utc().rfc3339()
+                        INFO("time                : %s", ts);
                         INFO("az                  : %.2f\xC2\xB0", ob.az_deg);
                         INFO("el                  : %.2f\xC2\xB0", ob.el_deg);
                         INFO("range               : %.0f km", ob.range_km);
