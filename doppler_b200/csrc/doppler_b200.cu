@@ -1,10 +1,11 @@
 // doppler_b200.cu -- C ABI (include/doppler_b200.h) over the sm_100a mixer kernels.
 //
 // Host side of the drop-in boundary: validates like the reference asserts (dsp.rs:87,103),
-// plans the samplenum state machine analytically (plan.h), keeps per-shift phasor tables in a
-// device arena, and drives the kernels either on caller-owned device buffers or on host
-// buffers through a 3-slot pinned/stream pipeline (H2D, kernel and D2H of neighbouring chunks
-// overlap).  No CPU implementation of the mixer exists in this library.
+// plans the samplenum state machine analytically (plan.h), cuts every launch into GRID / COLUMN
+// segments (mixer_kernels.cuh), keeps the phasor tables of short periods in a small device arena,
+// and drives the kernels either on caller-owned device buffers or on host buffers through a
+// 3-slot pinned/stream pipeline (H2D, kernel and D2H of neighbouring chunks overlap).  No CPU
+// implementation of the mixer exists in this library.
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
