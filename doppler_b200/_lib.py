@@ -44,6 +44,27 @@ SIGNATURES = {
     "doppler_b200_samplenum_advance": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_float, ctypes.c_uint32, ctypes.c_uint64]),
     "doppler_b200_samplenum_advance_blocks": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
                                                                 ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64]),
+    "doppler_b200_slice_bounds": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64,
+                                                 ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    "doppler_b200_slice_seeds": (ctypes.c_int, [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32,
+                                                ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]),
+    "doppler_b200_multi_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "doppler_b200_multi_destroy": (None, [ctypes.c_void_p]),
+    "doppler_b200_multi_size": (ctypes.c_int, [ctypes.c_void_p]),
+    "doppler_b200_multi_ctx": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int]),
+    "doppler_b200_multi_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "doppler_b200_multi_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "doppler_b200_mix_multi": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_float, ctypes.c_uint32, u32p, ctypes.c_void_p, ctypes.c_size_t, szp]),
+    "doppler_b200_mix_blocks_multi": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                                     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint32, u32p,
+                                                     ctypes.c_void_p, ctypes.c_size_t, szp]),
+    "doppler_b200_mix_multi_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_float, ctypes.c_uint32, u32p, ctypes.c_void_p, ctypes.c_void_p]),
+    "doppler_b200_mix_blocks_multi_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                         ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint32, u32p,
+                                                         ctypes.c_void_p, ctypes.c_void_p]),
+    "doppler_b200_multi_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
     "doppler_b200_doppler_hz": (ctypes.c_double, [ctypes.c_double, ctypes.c_uint32]),
     "doppler_b200_track_shift": (ctypes.c_float, [ctypes.c_double, ctypes.c_int32]),
     "doppler_b200_replay_seconds": (ctypes.c_int64, [ctypes.c_uint64, ctypes.c_uint32]),

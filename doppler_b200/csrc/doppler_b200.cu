@@ -821,7 +821,7 @@ const char* doppler_b200_last_error(const doppler_b200_ctx* ctx) { return ctx ? 
 void* doppler_b200_host_alloc(size_t bytes)
 {
     void* p = nullptr;
-    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {   // portable: every device of a multi-GPU group DMAs from it
         cudaGetLastError();
         return nullptr;
     }
@@ -836,7 +836,7 @@ void doppler_b200_host_free(void* p)
 int doppler_b200_host_register(void* p, size_t bytes)
 {
     if (!p || bytes == 0) return DOPPLER_B200_EINVAL;
-    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
         cudaGetLastError();
         return DOPPLER_B200_ECUDA;
     }

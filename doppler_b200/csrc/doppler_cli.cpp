@@ -10,7 +10,8 @@
 // kIdleMicros, so a live 1 Msps pipe sees millisecond latency (the reference: one 8 KiB block) while
 // a fast producer fills 32 MiB chunks.
 //
-// Extensions (not in the reference): --device N; --doppler-table FILE (track replay from a text
+// Extensions (not in the reference): --device N; --devices A,B,... (every chunk is cut into contiguous time
+// slices, one per listed GPU, with analytically carried samplenum -- doppler_b200_mix_multi); --doppler-table FILE (track replay from a text
 // file of doppler_hz values, one per second of recording, instead of --tlefile/--tlename/
 // --location/--frequency).
 #include <errno.h>
@@ -77,6 +78,7 @@ struct Args {
     uint32_t frequency = 0;
     int32_t offset = 0;
     int device = 0;
+    std::vector<int> devices;   // --devices: time-slice every chunk across these GPUs
 };
 
 [[noreturn]] void usage_error(const char* fmt, ...)
@@ -107,7 +109,8 @@ void print_help(const char* sub)
                "OPTIONS:\n    -i, --intype <INTYPE>            IQ data input type [values: i16, f32]\n"
                "    -o, --outtype <OUTTYPE>          IQ data output type [values: i16, f32]\n"
                "    -s, --samplerate <SAMPLERATE>    IQ data samplerate\n        --shift <SHIFT>              frequency shift in Hz\n"
-               "        --device <N>                 CUDA device (default 0)\n");
+               "        --device <N>                 CUDA device (default 0)\n"
+               "        --devices <A,B,...>          time-slice the stream across these CUDA devices\n");
     } else {
         printf("doppler-track\nDoppler tracking mode\n\nUSAGE:\n    doppler track [OPTIONS] --samplerate <SAMPLERATE> --intype <INTYPE> --tlefile <TLEFILE> "
                "--tlename <TLENAME> --location <LOCATION> --frequency <FREQUENCY>\n\nOPTIONS:\n"
@@ -121,7 +124,8 @@ void print_help(const char* sub)
                "        --tlefile <TLEFILE>          TLE file: eg. http://www.celestrak.com/NORAD/elements/cubesat.txt\n"
                "        --tlename <TLENAME>          TLE name in TLE file: eg. ESTCUBE 1\n"
                "        --doppler-table <FILE>       (extension) doppler_hz per second of recording, replaces the TLE options\n"
-               "        --device <N>                 CUDA device (default 0)\n");
+               "        --device <N>                 CUDA device (default 0)\n"
+               "        --devices <A,B,...>          time-slice the stream across these CUDA devices (replay / const)\n");
     }
 }
 
@@ -245,6 +249,16 @@ Args parse_args(int argc, char** argv)
         else if (k == "-i" || k == "--intype") a.intype = parse_type("--intype <INTYPE>", need());
         else if (k == "-o" || k == "--outtype") a.outtype = parse_type("--outtype <OUTTYPE>", need());
         else if (k == "--device") a.device = parse_int<int>("DEVICE", need(), 0, 1023);
+        else if (k == "--devices") {
+            const std::string list = need();
+            size_t pos = 0;
+            while (pos <= list.size()) {
+                size_t comma = list.find(',', pos);
+                if (comma == std::string::npos) comma = list.size();
+                a.devices.push_back(parse_int<int>("DEVICES", list.substr(pos, comma - pos), 0, 1023));
+                pos = comma + 1;
+            }
+        }
         else if (!a.track && k == "--shift") {
             a.shift = parse_int<int32_t>("SHIFT", need(), -2147483648LL, 2147483647LL);
             have_shift = true;
@@ -384,6 +398,12 @@ void write_full(int fd, const uint8_t* buf, size_t len)
     exit(1);
 }
 
+[[noreturn]] void die_multi(doppler_b200_multi* m, const char* what, int rc)
+{
+    ERROR("%s failed (%d): %s", what, rc, doppler_b200_multi_last_error(m));
+    exit(1);
+}
+
 // Shift of pump block `b` in replay mode: the Doppler at the whole second reached by the samples
 // counted before block b-1 (main.rs:162-166, one-block lag), plus the offset (main.rs:177).
 struct ReplayClock {
@@ -499,12 +519,20 @@ int main(int argc, char** argv)
         return 1e3 * (double)(t.tv_sec - t_start.tv_sec) + 1e-3 * (double)(t.tv_usec - t_start.tv_usec);
     };
     doppler_b200_ctx* ctx = nullptr;
-    int rc = doppler_b200_create(args.device, &ctx);
+    doppler_b200_multi* multi = nullptr;
+    int rc;
+    if (chunked && args.devices.size() > 1) {
+        rc = doppler_b200_multi_create(args.devices.data(), (int)args.devices.size(), &multi);
+        if (rc == DOPPLER_B200_OK) ctx = doppler_b200_multi_ctx(multi, 0);
+    } else {
+        rc = doppler_b200_create(args.devices.size() == 1 ? args.devices[0] : args.device, &ctx);
+    }
     if (rc != DOPPLER_B200_OK) {
         ERROR("doppler_b200_create failed (%d): %s", rc, doppler_b200_last_error(nullptr));
         fflush(stderr);
         _exit(1);   // the reader thread may be blocked in read(2)
     }
+    if (multi) INFO("\ttime slices     : %d GPUs per chunk", doppler_b200_multi_size(multi));
     const double ms_create = since_start_ms();
 
     uint32_t samplenr = 0;   // main.rs:60
@@ -593,9 +621,15 @@ int main(int argc, char** argv)
         bytes_in += c.in_len;
         nchunks++;
         if (!args.track) {
-            rc = doppler_b200_mix(ctx, c.in, usable, args.intype, args.outtype, (float)args.shift /* main.rs:110 */, args.samplerate,
-                                  &samplenr, c.out, out_cap, &c.out_len);
-            if (rc) die_ctx(ctx, "doppler_b200_mix", rc);
+            if (multi) {
+                rc = doppler_b200_mix_multi(multi, c.in, usable, args.intype, args.outtype, (float)args.shift, args.samplerate, &samplenr,
+                                            c.out, out_cap, &c.out_len);
+                if (rc) die_multi(multi, "doppler_b200_mix_multi", rc);
+            } else {
+                rc = doppler_b200_mix(ctx, c.in, usable, args.intype, args.outtype, (float)args.shift /* main.rs:110 */, args.samplerate,
+                                      &samplenr, c.out, out_cap, &c.out_len);
+                if (rc) die_ctx(ctx, "doppler_b200_mix", rc);
+            }
         } else {
             const size_t nblocks = (usable + kBlock - 1) / kBlock;
             shifts.resize(nblocks ? nblocks : 1);
@@ -625,7 +659,11 @@ int main(int argc, char** argv)
                 }
                 shifts[b] = doppler_b200_track_shift(doppler_hz, args.offset);
             }
-            if (usable) {
+            if (usable && multi) {
+                rc = doppler_b200_mix_blocks_multi(multi, c.in, usable, args.intype, args.outtype, shifts.data(), nblocks, kBlock,
+                                                   args.samplerate, &samplenr, c.out, out_cap, &c.out_len);
+                if (rc) die_multi(multi, "doppler_b200_mix_blocks_multi", rc);
+            } else if (usable) {
                 rc = doppler_b200_mix_blocks(ctx, c.in, usable, args.intype, args.outtype, shifts.data(), nblocks, kBlock, args.samplerate,
                                              &samplenr, c.out, out_cap, &c.out_len);
                 if (rc) die_ctx(ctx, "doppler_b200_mix_blocks", rc);
@@ -656,6 +694,9 @@ int main(int argc, char** argv)
         free(c.in);
         free(c.out);
     }
-    doppler_b200_destroy(ctx);
+    if (multi)
+        doppler_b200_multi_destroy(multi);
+    else
+        doppler_b200_destroy(ctx);
     return exit_code;
 }

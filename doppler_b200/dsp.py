@@ -145,6 +145,110 @@ class Mixer:
         return s, c
 
 
+class MultiMixer:
+    """A group of contexts, one per GPU of the box (include/doppler_b200.h: doppler_b200_multi_create).  One stream is
+    cut into contiguous time slices on pump-block boundaries, slice d goes to device d; no collective."""
+
+    def __init__(self, devices=None):
+        self._lib = _lib.load()
+        self._m = ctypes.c_void_p()
+        if devices is None:
+            rc = self._lib.doppler_b200_multi_create(None, 0, ctypes.byref(self._m))
+        else:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self._lib.doppler_b200_multi_create(arr, len(devices), ctypes.byref(self._m))
+        if rc != OK:
+            raise DopplerError(rc, self._lib.doppler_b200_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.doppler_b200_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self._lib.doppler_b200_multi_size(self._m))
+
+    def _check(self, rc):
+        if rc != OK:
+            raise DopplerError(rc, self._lib.doppler_b200_multi_last_error(self._m).decode())
+
+    @property
+    def launch_count(self):
+        return int(self._lib.doppler_b200_multi_launch_count(self._m))
+
+    def synchronize(self):
+        self._check(self._lib.doppler_b200_multi_synchronize(self._m))
+
+    def mix(self, inbuf, intype, outtype, shift_hz, samplerate, samplenum=0):
+        a = _as_bytes_array(inbuf)
+        out = np.empty((a.size // _BPS[intype]) * _BPS[outtype], dtype=np.uint8)
+        sn = ctypes.c_uint32(samplenum)
+        n = ctypes.c_size_t(0)
+        self._check(self._lib.doppler_b200_mix_multi(self._m, _ptr(a), a.size, intype, outtype, ctypes.c_float(shift_hz),
+                                                     int(samplerate), ctypes.byref(sn), _ptr(out), out.size, ctypes.byref(n)))
+        return out[:n.value], sn.value
+
+    def mix_blocks(self, inbuf, intype, outtype, shifts_hz, samplerate, samplenum=0, block_bytes=BUFFER_SIZE):
+        a = _as_bytes_array(inbuf)
+        sh = np.ascontiguousarray(shifts_hz, dtype=np.float32)
+        out = np.empty((a.size // _BPS[intype]) * _BPS[outtype], dtype=np.uint8)
+        sn = ctypes.c_uint32(samplenum)
+        n = ctypes.c_size_t(0)
+        self._check(self._lib.doppler_b200_mix_blocks_multi(self._m, _ptr(a), a.size, intype, outtype, _ptr(sh), sh.size, block_bytes,
+                                                            int(samplerate), ctypes.byref(sn), _ptr(out), out.size, ctypes.byref(n)))
+        return out[:n.value], sn.value
+
+    def _slices(self, d_in, in_len, d_out, out_cap):
+        k = len(self)
+        if not (len(d_in) == len(in_len) == len(d_out) == len(out_cap) == k):
+            raise DopplerError(EINVAL, f"need one slice per device ({k})")
+        return ((ctypes.c_void_p * k)(*d_in), (ctypes.c_size_t * k)(*in_len), (ctypes.c_void_p * k)(*d_out), (ctypes.c_size_t * k)(*out_cap))
+
+    def mix_dev(self, d_in, in_len, intype, outtype, shift_hz, samplerate, samplenum, d_out, out_cap):
+        """Device-resident slices: lists of per-device pointers / byte lengths.  Returns the final samplenum."""
+        pi, li, po, lo = self._slices(d_in, in_len, d_out, out_cap)
+        sn = ctypes.c_uint32(samplenum)
+        self._check(self._lib.doppler_b200_mix_multi_dev(self._m, pi, li, intype, outtype, ctypes.c_float(shift_hz), int(samplerate),
+                                                         ctypes.byref(sn), po, lo))
+        return sn.value
+
+    def mix_blocks_dev(self, d_in, in_len, intype, outtype, shifts_hz, samplerate, samplenum, d_out, out_cap, block_bytes=BUFFER_SIZE):
+        pi, li, po, lo = self._slices(d_in, in_len, d_out, out_cap)
+        sh = np.ascontiguousarray(shifts_hz, dtype=np.float32)
+        sn = ctypes.c_uint32(samplenum)
+        self._check(self._lib.doppler_b200_mix_blocks_multi_dev(self._m, pi, li, intype, outtype, _ptr(sh), sh.size, block_bytes,
+                                                                int(samplerate), ctypes.byref(sn), po, lo))
+        return sn.value
+
+
+def slice_bounds(total_samples, nslices, index, block_samples):
+    """[begin, end) of time slice `index` (doppler_b200_slice_bounds)."""
+    b, e = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    rc = _lib.load().doppler_b200_slice_bounds(int(total_samples), int(nslices), int(index), int(block_samples), ctypes.byref(b), ctypes.byref(e))
+    if rc != OK:
+        raise DopplerError(rc, "bad slice_bounds arguments")
+    return b.value, e.value
+
+
+def slice_seeds(samplenum, shifts_hz, block_samples, samplerate, total_samples, nslices):
+    """(begins, seeds), nslices + 1 entries each: first sample of every time slice and the reference's samplenum there
+    (doppler_b200_slice_seeds).  One shift value = const mode."""
+    sh = np.ascontiguousarray(np.atleast_1d(shifts_hz), dtype=np.float32)
+    begins = np.zeros(nslices + 1, dtype=np.uint64)
+    seeds = np.zeros(nslices + 1, dtype=np.uint32)
+    rc = _lib.load().doppler_b200_slice_seeds(int(samplenum), _ptr(sh), sh.size, int(block_samples), int(samplerate), int(total_samples),
+                                              int(nslices), _ptr(begins), _ptr(seeds))
+    if rc != OK:
+        raise DopplerError(rc, "bad slice_seeds arguments")
+    return [int(x) for x in begins], [int(x) for x in seeds]
+
+
 # ---- host-only analytic samplenum (no GPU needed) ------------------------------------------
 
 def samplenum_advance(samplenum, shift_hz, samplerate, count):

@@ -4,7 +4,9 @@ The path shards with no exchange step: contiguous slices aligned to the referenc
 pump block (/root/reference/src/main.rs:49) so that the per-block shift schedule of track mode
 (main.rs:177) stays aligned, and the only cross-slice state -- the reference's `samplenum`
 (main.rs:60) at the first sample of the slice -- is computed analytically on the host.
-Host-only logic: no GPU needed (covered by the world_size-2 gloo test).
+Host-only logic: no GPU needed (covered by the world_size-2 gloo test).  Thin caller of the C ABI
+(doppler_b200_slice_bounds / _slice_seeds / _samplenum_advance*): the partition lives in the
+library, where the CLI (--devices) and doppler_b200_mix_multi use the same rule.
 """
 from . import dsp
 
@@ -19,15 +21,7 @@ def block_samples(intype):
 def slice_bounds(total_samples, world_size, rank, intype):
     """[begin, end) of `rank`'s slice: whole pump blocks, remainder blocks to the lowest ranks,
     the ragged tail (a short last block) to the last rank."""
-    bs = block_samples(intype)
-    nblocks = total_samples // bs
-    per, extra = divmod(nblocks, world_size)
-    b0 = rank * per + min(rank, extra)
-    b1 = b0 + per + (1 if rank < extra else 0)
-    begin, end = b0 * bs, b1 * bs
-    if rank == world_size - 1:
-        end = total_samples
-    return begin, end
+    return dsp.slice_bounds(total_samples, world_size, rank, block_samples(intype))   # the C entry: one rule for every caller
 
 
 def seed_const(shift_hz, samplerate, begin):
@@ -38,3 +32,8 @@ def seed_const(shift_hz, samplerate, begin):
 def seed_blocks(shifts_hz, intype, samplerate, begin):
     """samplenum at stream sample `begin` for a per-block shift schedule (track mode)."""
     return dsp.samplenum_advance_blocks(0, shifts_hz, block_samples(intype), samplerate, begin)
+
+
+def plan(shifts_hz, intype, samplerate, total_samples, world_size, samplenum=0):
+    """(begins, seeds) of all `world_size` slices in one call (doppler_b200_slice_seeds); a scalar shift = const mode."""
+    return dsp.slice_seeds(samplenum, shifts_hz, block_samples(intype), samplerate, total_samples, world_size)

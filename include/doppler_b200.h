@@ -135,6 +135,54 @@ uint32_t doppler_b200_samplenum_advance(uint32_t samplenum, float shift_hz, uint
 uint32_t doppler_b200_samplenum_advance_blocks(uint32_t samplenum, const float* shift_hz_per_block, size_t nblocks,
                                                uint64_t block_samples, uint32_t samplerate, uint64_t count);
 
+/* ---- time-sliced multi-GPU (one stream over several devices of one box, no collective) ------ */
+
+/* The path shards with no exchange step: the stream is cut into contiguous slices on whole pump
+ * blocks (main.rs:49, so the per-block shift of track mode, main.rs:177, stays aligned) and the
+ * only cross-slice state -- `samplenum` (main.rs:60) at each slice's first sample -- is carried
+ * analytically on the host.  The reference is single-threaded and has no equivalent; these
+ * entries make the partition part of the product instead of every caller's job. */
+
+/* [begin, end) in samples of slice `index` of `nslices`: whole blocks of `block_samples`, the
+ * remainder blocks to the lowest slices, the ragged tail (a short last block) to the last slice. */
+int doppler_b200_slice_bounds(uint64_t total_samples, uint32_t nslices, uint32_t index, uint64_t block_samples,
+                              uint64_t* begin, uint64_t* end);
+
+/* begins[i] / seeds[i], i = 0..nslices: first sample of slice i and the reference's samplenum
+ * there (begins[nslices] = total_samples, seeds[nslices] = the state after the stream), for a
+ * per-block shift schedule; nblocks == 1 means one shift for the whole stream (const mode). */
+int doppler_b200_slice_seeds(uint32_t samplenum, const float* shift_hz_per_block, size_t nblocks, uint64_t block_samples,
+                             uint32_t samplerate, uint64_t total_samples, uint32_t nslices, uint64_t* begins, uint32_t* seeds);
+
+/* A group of contexts, one per device, each driven by its own host thread.  devices == NULL:
+ * ordinals 0..ndevices-1; ndevices == 0: every visible device. */
+typedef struct doppler_b200_multi doppler_b200_multi;
+int doppler_b200_multi_create(const int* devices, int ndevices, doppler_b200_multi** out);
+void doppler_b200_multi_destroy(doppler_b200_multi* m);
+int doppler_b200_multi_size(const doppler_b200_multi* m);
+doppler_b200_ctx* doppler_b200_multi_ctx(doppler_b200_multi* m, int index);
+const char* doppler_b200_multi_last_error(const doppler_b200_multi* m);
+uint64_t doppler_b200_multi_launch_count(const doppler_b200_multi* m);
+
+/* doppler_b200_mix / _mix_blocks over all devices of the group: host buffers, slice d through
+ * device d's own H2D / kernel / D2H pipeline, all slices concurrently.  Same arguments, same
+ * result bytes and the same final *samplenum as the single-device calls. */
+int doppler_b200_mix_multi(doppler_b200_multi* m, const void* in, size_t in_len, int intype, int outtype, float shift_hz,
+                           uint32_t samplerate, uint32_t* samplenum, void* out, size_t out_cap, size_t* out_len);
+int doppler_b200_mix_blocks_multi(doppler_b200_multi* m, const void* in, size_t in_len, int intype, int outtype,
+                                  const float* shift_hz_per_block, size_t nblocks, size_t block_bytes, uint32_t samplerate,
+                                  uint32_t* samplenum, void* out, size_t out_cap, size_t* out_len);
+
+/* Device-resident slices: d_in[d] / d_out[d] live on device d (16-byte aligned), in_len[d] bytes
+ * each, consecutive in stream order; with a schedule every slice but the last non-empty one must be
+ * whole blocks.  Asynchronous on each context's own stream (doppler_b200_multi_synchronize). */
+int doppler_b200_mix_multi_dev(doppler_b200_multi* m, const void* const* d_in, const size_t* in_len, int intype, int outtype,
+                               float shift_hz, uint32_t samplerate, uint32_t* samplenum, void* const* d_out, const size_t* out_cap);
+int doppler_b200_mix_blocks_multi_dev(doppler_b200_multi* m, const void* const* d_in, const size_t* in_len, int intype, int outtype,
+                                      const float* shift_hz_per_block, size_t nblocks, size_t block_bytes, uint32_t samplerate,
+                                      uint32_t* samplenum, void* const* d_out, const size_t* out_cap);
+int doppler_b200_multi_synchronize(doppler_b200_multi* m);
+
 /* ---- track mode's Doppler schedule (host only, no GPU needed) ------------------------------ */
 
 /* src/main.rs:163: doppler_hz = (range_rate_km_sec * 1000 / c) * frequency * (-1), in f64. */
