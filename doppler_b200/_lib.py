@@ -24,6 +24,8 @@ SIGNATURES = {
     "doppler_b200_host_free": (None, [ctypes.c_void_p]),
     "doppler_b200_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
     "doppler_b200_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
+    "doppler_b200_libm_compatible": (ctypes.c_int, []),
+    "doppler_b200_libm_mismatches": (ctypes.c_uint32, [ctypes.c_void_p]),
     "doppler_b200_launch_count": (ctypes.c_uint64, [c_ctx]),
     "doppler_b200_convert_iqi16_to_complex": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "doppler_b200_convert_iqf32_to_complex": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
@@ -85,6 +87,8 @@ SIGNATURES = {
     "doppler_b200_plan_tiles_trace": (ctypes.c_long, [ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
                                                       ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32,
                                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "doppler_b200_pipeline_probe": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                   ctypes.c_size_t]),
     "doppler_b200_phasor_probe": (ctypes.c_int, [c_ctx, ctypes.c_float, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_void_p,
                                                  ctypes.c_void_p]),
     "doppler_b200_sincosf_probe": (ctypes.c_int, [c_ctx, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_size_t,

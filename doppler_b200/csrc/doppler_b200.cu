@@ -64,13 +64,13 @@ constexpr uint32_t kUnitsPerPipe = 16;               // ... halved until the lau
 constexpr uint32_t kColumnMinRows = 2;               // fewer whole periods than this: evaluate per sample instead
 constexpr uint32_t kColumnMinLaunch = 4u << 20;      // launches below this many samples are latency-bound: a serial window
                                                      // evaluation per work unit costs more than it saves (measured 23 vs 13 us at 1 M)
-constexpr size_t kArenaMaxEntries = 64ull << 20;     // 512 MiB of (cos, sin) pairs
+constexpr size_t kArenaEntries = 4ull << 20;         // 32 MiB of (cos, sin) pairs: >= 1000 tables of the longest tabled period
 constexpr uint32_t kSmemTabMaxEntries = 4096;        // 32 KiB of shared memory per CTA at most
 constexpr size_t kHostChunkBytes = 32ull << 20;      // host-path pipeline chunk (input side)
 constexpr int kSlots = 3;
 constexpr int kMetaSlots = 8;                        // pinned staging slots for launch metadata
 
-std::string g_create_error;
+thread_local std::string g_create_error;   // create() errors, read back by the calling thread through last_error(NULL)
 
 struct TableRef {
     uint32_t off;
@@ -238,21 +238,17 @@ int get_table(doppler_b200_ctx* ctx, float r, uint32_t period, uint64_t piece_le
     }
     if (piece_len < 2ull * period) return DOPPLER_B200_OK;   // fewer reuses than entries: evaluate directly
     const size_t entries = (size_t)period + dmix::kTabPad;
+    if (!ctx->arena) {
+        CUDA_TRY(ctx, cudaMalloc(&ctx->arena, kArenaEntries * sizeof(float2)));
+        ctx->arena_cap = kArenaEntries;
+    }
     if (ctx->arena_used + entries > ctx->arena_cap) {
-        // grow (or recycle) the arena; cached tables are dropped, in-flight readers drained first
+        // Recycle in place: the arena is a fixed block allocated once, so a stream that forms a new ratio per
+        // block for hours (realtime track mode) never pays a free / malloc.  Launches that still read the old
+        // tables are drained first -- one device-wide wait per >= 1000 table builds.
         CUDA_TRY(ctx, cudaDeviceSynchronize());
-        size_t want = std::max<size_t>(ctx->arena_cap * 2, std::max<size_t>(entries * 2, 1u << 20));
-        want = std::min(want, kArenaMaxEntries);
-        if (want > ctx->arena_cap) {
-            if (ctx->arena) CUDA_TRY(ctx, cudaFree(ctx->arena));
-            ctx->arena = nullptr;
-            ctx->arena_cap = 0;
-            CUDA_TRY(ctx, cudaMalloc(&ctx->arena, want * sizeof(float2)));
-            ctx->arena_cap = want;
-        }
         ctx->arena_used = 0;
         ctx->tables.clear();
-        if (entries > ctx->arena_cap) return DOPPLER_B200_OK;
     }
     const uint32_t off = (uint32_t)ctx->arena_used;
     const uint32_t blocks = (uint32_t)((entries + dmix::kThreads - 1) / dmix::kThreads);
@@ -453,7 +449,8 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
 {
     if (nsamples == 0) return DOPPLER_B200_OK;
     std::vector<dplan::Piece> pieces;
-    ctx->planner.plan(runs, 0, samplenum, &pieces);
+    uint32_t sn_after = *samplenum;   // committed only when every launch has been enqueued
+    ctx->planner.plan(runs, 0, &sn_after, &pieces);
 
     const StreamShape& shapes = shape_for(intype, outtype);
     const size_t ibps = bytes_per_sample(intype), obps = bytes_per_sample(outtype);
@@ -468,6 +465,10 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         std::vector<DevPiece> dev;
         std::vector<const dplan::Piece*> src;
         std::vector<uint64_t> dev_len;
+        // DevPiece::step_u is baked from the row width, which depends on the type pair only (kRow = 32 * G): one value serves all three shapes
+        static_assert(SegI16I16::kRow == 128 && SegI16F32::kRow == 64 && SegF32I16::kRow == 64 && SegF32F32::kRow == 64, "row width per type pair");
+        if (shapes.grid.row_samples != shapes.seg.row_samples || shapes.grid.row_samples != shapes.direct.row_samples)
+            return fail(ctx, DOPPLER_B200_EINVAL, "kernel shapes of one type pair disagree on the row width");
         clip_pieces(pieces, l0, l1, shapes.grid.row_samples, &dev, &src);
         for (size_t i = 0; i < dev.size(); i++) {
             dev_len.push_back(dev[i].k_end - dev[i].k_begin);
@@ -579,6 +580,7 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
             meta_slot->used = true;
         }
     }
+    *samplenum = sn_after;
     return DOPPLER_B200_OK;
 }
 
@@ -668,11 +670,25 @@ int retire_slot(doppler_b200_ctx* ctx, Slot& sl)
     return DOPPLER_B200_OK;
 }
 
+// After a failed host-path call: nothing may stay in flight into the caller's buffers, and no slot may keep a
+// pending copy-out into memory the caller is free to release once the call has returned.
+void abandon_slots(doppler_b200_ctx* ctx)
+{
+    for (Slot& sl : ctx->slots) {
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        sl.user_out = nullptr;
+        sl.user_out_bytes = 0;
+        sl.busy = false;
+    }
+    cudaGetLastError();
+}
+
 // Host-buffer pipeline: chunk c uses slot c % kSlots; each slot has its own stream so the H2D
-// of chunk c+1 overlaps the kernel of chunk c and the D2H of chunk c-1.
-int mix_host(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int intype, int outtype,
-             const float* shifts, size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint32_t* samplenum,
-             void* out)
+// of chunk c+1 overlaps the kernel of chunk c and the D2H of chunk c-1.  `copy_only` skips the
+// kernel (doppler_b200_pipeline_probe: the ceiling the platform's host memory / PCIe path sets).
+int mix_host_run(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int intype, int outtype,
+                 const float* shifts, size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint32_t* samplenum,
+                 void* out, bool copy_only)
 {
     const size_t ibps = bytes_per_sample(intype), obps = bytes_per_sample(outtype);
     // chunk = whole number of shift blocks and of the largest tile
@@ -700,15 +716,17 @@ int mix_host(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int intyp
             src = static_cast<const char*>(sl.h_in);
         }
         CUDA_TRY(ctx, cudaMemcpyAsync(sl.d_in, src, n * ibps, cudaMemcpyHostToDevice, sl.stream));
-        std::vector<dplan::Run> runs;
-        if (nblocks <= 1 || block_samples == 0) {
-            runs.push_back(dplan::Run{n, dplan::ratio(shifts[0], samplerate)});
-        } else {
-            const size_t b0 = (size_t)(k / block_samples);
-            runs = dplan::runs_from_blocks(shifts + b0, nblocks - b0, block_samples, samplerate, n);
+        if (!copy_only) {
+            std::vector<dplan::Run> runs;
+            if (nblocks <= 1 || block_samples == 0) {
+                runs.push_back(dplan::Run{n, dplan::ratio(shifts[0], samplerate)});
+            } else {
+                const size_t b0 = (size_t)(k / block_samples);
+                runs = dplan::runs_from_blocks(shifts + b0, nblocks - b0, block_samples, samplerate, n);
+            }
+            rc = launch_mix(ctx, sl.d_in, sl.d_out, n, intype, outtype, runs, &sn, sl.stream);
+            if (rc) return rc;
         }
-        rc = launch_mix(ctx, sl.d_in, sl.d_out, n, intype, outtype, runs, &sn, sl.stream);
-        if (rc) return rc;
         char* dst = static_cast<char*>(out) + k * obps;
         if (out_pinned) {
             CUDA_TRY(ctx, cudaMemcpyAsync(dst, sl.d_out, n * obps, cudaMemcpyDeviceToHost, sl.stream));
@@ -727,6 +745,18 @@ int mix_host(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int intyp
     }
     *samplenum = sn;
     return DOPPLER_B200_OK;
+}
+
+int mix_host(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int intype, int outtype, const float* shifts,
+             size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint32_t* samplenum, void* out, bool copy_only = false)
+{
+    const int rc = mix_host_run(ctx, in, nsamples, intype, outtype, shifts, nblocks, block_samples, samplerate, samplenum, out, copy_only);
+    if (rc) {
+        const std::string keep = ctx->err;   // the first error is the one to report
+        abandon_slots(ctx);
+        ctx->err = keep;
+    }
+    return rc;
 }
 
 int check_blocks(doppler_b200_ctx* ctx, size_t in_len, int intype, const float* shifts, size_t nblocks, size_t block_bytes,
@@ -765,6 +795,17 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     if (prop.major != 10)
         return fail(nullptr, DOPPLER_B200_ENODEV, "device %d is sm_%d%d; this build carries sm_100a code only", device,
                     prop.major, prop.minor);
+    if (!doppler_b200_libm_compatible()) {
+        // numerics contract: the device reproduces glibc's __sincosf_fma; this host's libm differs
+        if (getenv("DOPPLER_B200_STRICT_LIBM") && atoi(getenv("DOPPLER_B200_STRICT_LIBM")) != 0)
+            return fail(nullptr, DOPPLER_B200_ELIBM, "host libm sincosf differs from the glibc __sincosf_fma sequence the device reproduces");
+        static bool warned = false;
+        if (!warned) {
+            warned = true;
+            fprintf(stderr, "doppler_b200: warning: this host's libm sincosf is not bit-identical to glibc x86-64 __sincosf_fma; GPU output "
+                            "matches that variant, not the reference built on this host (doppler_b200_libm_compatible() == 0)\n");
+        }
+    }
     CUDA_TRY(nullptr, cudaSetDevice(device));
     doppler_b200_ctx* ctx = new (std::nothrow) doppler_b200_ctx;
     if (!ctx) return fail(nullptr, DOPPLER_B200_ENOMEM, "out of host memory");
@@ -924,6 +965,17 @@ int doppler_b200_mix_blocks(doppler_b200_ctx* ctx, const void* in, size_t in_len
     return rc;
 }
 
+int doppler_b200_pipeline_probe(doppler_b200_ctx* ctx, const void* in, size_t in_len, int intype, int outtype, void* out, size_t out_cap)
+{
+    uint64_t n = 0;
+    uint32_t sn = 0;
+    int rc = check_common(ctx, in, in_len, intype, outtype, &sn, out, out_cap, &n);
+    if (rc || n == 0) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const float zero = 0.0f;
+    return mix_host(ctx, in, n, intype, outtype, &zero, 1, 0, 1, &sn, out, /*copy_only=*/true);
+}
+
 // ---- the reference's three functions, one to one ---------------------------------------------
 
 int doppler_b200_shift_frequency(doppler_b200_ctx* ctx, const float* inbuf, size_t nsamples, uint32_t* samplenum,
@@ -949,8 +1001,12 @@ static int convert_host(doppler_b200_ctx* ctx, const uint8_t* inbuf, size_t len,
     for (uint64_t k = 0; k < n; k += chunk) {
         const uint64_t m = std::min(chunk, n - k);
         Slot& sl = ctx->slots[0];
-        int rc = ensure_slot(ctx, sl, std::min(chunk, n) * ibps, std::min(chunk, n) * 8);
-        if (rc) return rc;
+        int rc = retire_slot(ctx, sl);   // a pending copy-out of an earlier call must not outlive the buffers ensure_slot may replace
+        if (rc == DOPPLER_B200_OK) rc = ensure_slot(ctx, sl, std::min(chunk, n) * ibps, std::min(chunk, n) * 8);
+        if (rc) {
+            abandon_slots(ctx);
+            return rc;
+        }
         CUDA_TRY(ctx, cudaMemcpyAsync(sl.d_in, inbuf + k * ibps, m * ibps, cudaMemcpyHostToDevice, sl.stream));
         const uint32_t grid = (uint32_t)std::min<uint64_t>((m + dmix::kThreads - 1) / dmix::kThreads, (uint64_t)ctx->sm_count * 32);
         if (intype == DOPPLER_B200_I16)

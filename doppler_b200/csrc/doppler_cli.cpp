@@ -639,11 +639,14 @@ int main(int argc, char** argv)
                 if (use_tracker) {
                     const dorbit::Observation ob = tracker.observe_cached((double)args.start_unix + (double)sec);
                     doppler_hz = doppler_b200_doppler_hz(ob.range_rate_km_s, args.frequency);
-                    if (sec - last_logged_second >= 5) {   // main.rs:167-175
-                        last_logged_second = sec;
+                    // main.rs:166-169: dt is advanced BEFORE the telemetry test, so the 5 s cadence and the printed time
+                    // follow the updated dt while az / el / range / doppler are those of the update made at the old dt
+                    const int64_t sec_new = clock.second_of_block(block0 + b + 1);
+                    if (sec_new - last_logged_second >= 5) {   // main.rs:167-175
+                        last_logged_second = sec_new;
                         char ts[40];
                         struct tm gm;
-                        const time_t tt = (time_t)(args.start_unix + sec);
+                        const time_t tt = (time_t)(args.start_unix + sec_new);
                         gmtime_r(&tt, &gm);
                         strftime(ts, sizeof ts, "%Y-%m-%dT%H:%M:%SZ", &gm);   // (start_time + dt).to_utc().rfc3339()
                         INFO("time                : %s", ts);

@@ -50,7 +50,7 @@ struct DevPiece {          // launch-relative sample indices
     uint32_t tab;          // first entry of this piece's phasor table in the arena, or kNoTab
     uint32_t magic;        // division by `period`: q = (x * magic) >> shift for x < 2^31
     uint32_t shift;
-    uint32_t step_u;       // (CTA threads * G) mod period
+    uint32_t step_u;       // samples per warp-row (32 * G, a property of the type pair) mod period
     uint32_t pad[3];
 };
 static_assert(sizeof(DevPiece) == 48, "DevPiece layout");

@@ -442,7 +442,7 @@ struct doppler_b200_tracker {
     std::string err;
 };
 
-static std::string g_tracker_error;
+static thread_local std::string g_tracker_error;   // per calling thread, like errno
 
 extern "C" {
 

@@ -95,8 +95,27 @@ __attribute__((target("avx512f"))) static uint64_t first_hit_avx512(float r, uin
 }
 #endif
 
+// n in [2^31, 2^32): f32(n) takes one value per 256 consecutive n (ulp = 2^8, ties to the even mantissa), and the
+// reset test depends on n only through f32(n): one test per plateau instead of one per n.  Without this a ratio
+// that does not reset before the u32 wrap (tiny |r|) costs 2^31 scalar tests -- seconds of host time inside plan().
+static uint64_t first_hit_plateaus(float r, uint32_t n0, uint64_t limit)
+{
+    uint64_t done = 0;
+    while (done < limit) {
+        const uint32_t n = n0 + (uint32_t)done;   // >= 2^31 by contract; n0 + limit <= 2^32
+        if (hit(r, n)) return done;
+        const uint64_t v = (uint64_t)(float)n;                          // the plateau's value: a multiple of 256, up to 2^32
+        uint64_t last = v + (((v >> 8) & 1) ? 127 : 128);               // largest n rounding to v (the tie goes to the even mantissa)
+        if (last > 0xffffffffull) last = 0xffffffffull;
+        done += last + 1 - n;
+    }
+    return limit;
+}
+
 uint64_t first_hit(float r, uint32_t n0, uint64_t limit)
 {
+    // a non-finite ratio never hits (Inf * n is Inf or NaN, dsp.rs:125 fract() of those is NaN): no scan
+    if (!(r - r == 0.0f)) return limit;
     uint64_t done = 0;
 #if defined(__x86_64__) && defined(__GNUC__)
     static const int isa = __builtin_cpu_supports("avx512f") ? 2 : __builtin_cpu_supports("avx2") ? 1 : 0;
@@ -120,7 +139,7 @@ uint64_t first_hit(float r, uint32_t n0, uint64_t limit)
 #endif
         const uint64_t room = 0x100000000ull - nb;   // up to the u32 wrap
         if (span > room) span = room;
-        const uint64_t d = first_hit_scalar(r, nb, span);
+        const uint64_t d = nb >= 0x80000000u ? first_hit_plateaus(r, nb, span) : first_hit_scalar(r, nb, span);
         if (d < span) return done + d;
         done += span;
     }

@@ -17,9 +17,11 @@
 // every `a + b*c` of the C source is ONE fused operation; this file spells each fused /
 // unfused operation explicitly so no compiler flag can change it.
 //
-// Verified: tests/native/sincosf_hostcheck.c compares db_sincosf_glibc() against the host's
-// libm sincosf over all 2^32 float bit patterns (bit-identical, NaN payloads aside);
-// tests/test_gpu_sincosf.py does the same on the device over every theta the mixer forms.
+// Verified: tests/native/sincosf_hostcheck.cpp (driven by tests/test_sincosf_host.py) compares
+// db_sincosf_glibc() against the host's libm sincosf over all 2^32 float bit patterns (bit-identical,
+// NaN payloads aside; DOPPLER_FULL_SWEEP=1, strided by default);
+// tests/test_gpu_parity.py::test_device_sincosf_matches_host_libm does the same on the device, and
+// libm_guard.cpp re-checks a sample of it at run time (doppler_b200_libm_compatible).
 #pragma once
 #include <stdint.h>
 

@@ -14,7 +14,7 @@ I16 = 0  # usage.rs:39-42 DataType::I16
 F32 = 1  # usage.rs:39-42 DataType::F32
 BUFFER_SIZE = 8192  # main.rs:49
 
-OK, EINVAL, EALIGN, ECAP, ECUDA, ENODEV, ENOMEM = range(7)
+OK, EINVAL, EALIGN, ECAP, ECUDA, ENODEV, ENOMEM, ELIBM = range(8)
 _BPS = {I16: 4, F32: 8}
 
 
@@ -225,6 +225,11 @@ class MultiMixer:
         self._check(self._lib.doppler_b200_mix_blocks_multi_dev(self._m, pi, li, intype, outtype, _ptr(sh), sh.size, block_bytes,
                                                                 int(samplerate), ctypes.byref(sn), po, lo))
         return sn.value
+
+
+def libm_compatible():
+    """True when this host's libm sincosf is the variant the device reproduces (doppler_b200_libm_compatible)."""
+    return bool(_lib.load().doppler_b200_libm_compatible())
 
 
 def slice_bounds(total_samples, nslices, index, block_samples):

@@ -53,6 +53,8 @@ extern "C" {
 #define DOPPLER_B200_ECUDA 4  /* CUDA runtime error (see doppler_b200_last_error) */
 #define DOPPLER_B200_ENODEV 5 /* no usable sm_100 device / driver */
 #define DOPPLER_B200_ENOMEM 6
+#define DOPPLER_B200_ELIBM 7  /* DOPPLER_B200_STRICT_LIBM=1 and the host libm's sincosf is not the variant the device
+                                 reproduces (doppler_b200_libm_compatible) */
 
 typedef struct doppler_b200_ctx doppler_b200_ctx;
 
@@ -65,6 +67,18 @@ int doppler_b200_abi_version(void);
  * samplenum planner cache. */
 int doppler_b200_create(int device, doppler_b200_ctx** ctx_out);
 void doppler_b200_destroy(doppler_b200_ctx* ctx);
+
+/* Numerics guard.  Output parity with the reference means parity with the HOST libm's sincosf
+ * (complex.c:35); the device reproduces glibc >= 2.28 x86-64 `__sincosf_fma`.  Returns 1 when the
+ * host twin of the device routine agrees bit for bit with this host's sincosf on ~20 000 probes
+ * spanning every range of the algorithm, 0 otherwise (another libm, or glibc's non-FMA variant on a
+ * CPU without FMA: the GPU output is then still glibc-FMA-exact, but no longer "what the reference
+ * prints on this box").  Evaluated once per process; doppler_b200_create warns on stderr when it is 0
+ * and fails with ELIBM under DOPPLER_B200_STRICT_LIBM=1.  Host only, no GPU needed. */
+int doppler_b200_libm_compatible(void);
+/* Same comparison against any sincosf-shaped function (NULL = the host libm's): number of probes
+ * that disagree.  Test hook. */
+uint32_t doppler_b200_libm_mismatches(void (*sincosf_fn)(float, float*, float*));
 
 /* Text of the last error on this context ("" if none).  ctx may be NULL for create() errors. */
 const char* doppler_b200_last_error(const doppler_b200_ctx* ctx);
@@ -250,6 +264,13 @@ long doppler_b200_plan_trace(uint32_t* samplenum, const float* shift_hz_per_bloc
 long doppler_b200_plan_tiles_trace(int intype, int outtype, uint32_t samplenum, const float* shift_hz_per_block,
                                    size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint64_t count,
                                    uint32_t npipes, uint32_t* trace, uint32_t* cover, uint64_t* stats);
+
+/* Measurement hook: the host-buffer pipeline of doppler_b200_mix (same chunks, slots, streams, staging rules)
+ * with the kernel SKIPPED: every chunk goes host -> device (in_len bytes) and the same number of samples'
+ * worth of `outtype` bytes comes device -> host (content unspecified).  Its rate is the ceiling the box's
+ * host memory / PCIe path sets for doppler_b200_mix on these buffers (bench.py: e2e.ceiling). */
+int doppler_b200_pipeline_probe(doppler_b200_ctx* ctx, const void* in, size_t in_len, int intype, int outtype, void* out,
+                                size_t out_cap);
 
 /* Device self-test hook: evaluates the kernel's phasor routine, (cos, sin) of
  * theta = (-2*PI) * (r * f32(n)) (dsp.rs:121-122), for n = n0 .. n0+count-1 into host arrays. */

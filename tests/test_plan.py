@@ -202,3 +202,48 @@ def test_trace_property_random_ratios(oracle):
         assert dsp.samplenum_advance(start, shift, fs, count) == sn_want
 
     prop()
+
+
+def test_upper_half_plateau_scan_matches_the_oracle(oracle):
+    """n >= 2^31: the planner tests one n per f32 plateau (256 wide, ties to even) -- same answers as the recurrence."""
+    fs = 1_000_000
+    r_hits_late = float(np.float32(2.0 ** -10 * (1 + 2.0 ** -20)) * np.float32(fs))   # r*f32(n) ~ 2^21: integer on ~1 plateau in 4
+    for shift in (r_hits_late, 1.0e-6, -3.3e-4):
+        for start in (2**31, 2**31 + 12345, 2**31 + 127, 2**31 + 128, 2**31 + 129, 2**32 - 70_000, 3 * 2**30 + 383):
+            want, sn_want = oracle.samplenum_trace(start, shift, fs, 100_000)
+            got, sn, _ = dsp.plan_trace(start, [shift], 100_000, fs, 100_000)
+            assert np.array_equal(got, want), (shift, start)
+            assert sn == sn_want
+
+
+def test_no_reset_before_the_wrap_is_planned_quickly():
+    """A ratio that cannot reset before samplenum wraps (|r| * 2^32 < 1): 2^31 scalar tests before, one per plateau now."""
+    import time
+    t0 = time.perf_counter()
+    sn = dsp.samplenum_advance(2**31, 1.0e-7, 4_000_000_000, 2**31 + 10)   # r = 2.5e-17
+    dt = time.perf_counter() - t0
+    assert sn == 10          # ... 2^32 wraps to 0, r*0 == 0 resets to 1, nine more samples
+    assert dt < 2.0, dt
+    t0 = time.perf_counter()
+    for shift in (float("inf"), float("nan")):
+        assert dsp.samplenum_advance(5, shift, 48000, 2**33) == (5 + 2**33) % 2**32   # never resets, never scans
+    assert time.perf_counter() - t0 < 0.5
+
+
+def test_libm_guard(oracle):
+    """The numerics guard: the host twin of the device sincosf against this host's libm (compatible here), and
+    against a deliberately different sincosf (detected)."""
+    import ctypes
+    import math
+    from doppler_b200 import _lib
+    lib = _lib.load()
+    assert dsp.libm_compatible()
+    assert lib.doppler_b200_libm_mismatches(None) == 0
+    CB = ctypes.CFUNCTYPE(None, ctypes.c_float, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float))
+
+    def other(y, s, c):   # double-precision sin/cos rounded to float: close, but not glibc's sincosf
+        s[0] = math.sin(y) if math.isfinite(y) else float("nan")
+        c[0] = math.cos(y) if math.isfinite(y) else float("nan")
+
+    cb = CB(other)
+    assert lib.doppler_b200_libm_mismatches(ctypes.cast(cb, ctypes.c_void_p)) > 0
