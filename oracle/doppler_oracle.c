@@ -356,16 +356,18 @@ static void* oracle_slice_run(void* p)
     oracle_c32 a[ORACLE_BUFFER_SIZE / 4], b[ORACLE_BUFFER_SIZE / 4];
     size_t ibps = s->intype == ORACLE_I16 ? 4 : 8, obps = s->outtype == ORACLE_I16 ? 4 : 8;
     size_t done = 0;
+    uint32_t sn = s->samplenum;   /* thread-local: the per-sample state update must not share a cache line with other threads' */
     while (done < s->nsamples) {
         /* the reference's own block size in samples (8192 bytes, main.rs:49) */
         size_t n = s->nsamples - done;
         size_t blk = ORACLE_BUFFER_SIZE / ibps;
         if (n > blk) n = blk;
         size_t out_len = 0;
-        oracle_block(s->in + done * ibps, n * ibps, s->intype, s->outtype, s->shift_hz, s->samplerate, &s->samplenum,
+        oracle_block(s->in + done * ibps, n * ibps, s->intype, s->outtype, s->shift_hz, s->samplerate, &sn,
                      s->out + done * obps, &out_len, a, b);
         done += n;
     }
+    s->samplenum = sn;
     return NULL;
 }
 
@@ -395,6 +397,73 @@ double oracle_bench_const(const uint8_t* in, size_t nsamples, int intype, int ou
     clock_gettime(CLOCK_MONOTONIC, &t1);
     free(sl);
     free(th);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+/* The same for a per-block shift schedule (track mode): `threads` contiguous runs of whole 8192-byte
+ * blocks, thread t seeded with the samplenum the sequential recurrence (dsp.rs:125-130) reaches at its
+ * first sample -- computed here by running that recurrence, not by the product's analytic planner, so
+ * the output is independent of the code under test.  Returns the elapsed seconds of the threaded mixing
+ * (seeding excluded); *samplenum is advanced to the state after the last sample. */
+typedef struct {
+    const uint8_t* in;
+    uint8_t* out;
+    size_t len;          /* bytes */
+    int intype, outtype;
+    const float* shifts;
+    size_t nshifts;
+    uint32_t samplerate;
+    uint32_t samplenum;
+    long rc;
+} oracle_blocks_slice;
+
+static void* oracle_blocks_run(void* p)
+{
+    oracle_blocks_slice* s = (oracle_blocks_slice*)p;
+    uint32_t sn = s->samplenum;   /* thread-local, see oracle_slice_run */
+    s->rc = oracle_mix_blocks(s->in, s->len, s->intype, s->outtype, s->shifts, s->nshifts, s->samplerate, &sn, s->out);
+    s->samplenum = sn;
+    return NULL;
+}
+
+double oracle_bench_blocks(const uint8_t* in, size_t nsamples, int intype, int outtype, const float* shifts, size_t nshifts,
+                           uint32_t samplerate, uint32_t* samplenum, uint8_t* out, int threads)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 1024) threads = 1024;
+    size_t ibps = intype == ORACLE_I16 ? 4 : 8, obps = outtype == ORACLE_I16 ? 4 : 8;
+    size_t blk = ORACLE_BUFFER_SIZE / ibps;
+    size_t nblocks = (nsamples + blk - 1) / blk;
+    if (nblocks > nshifts) return -1.0;
+    if ((size_t)threads > nblocks) threads = nblocks ? (int)nblocks : 1;
+    oracle_blocks_slice* sl = (oracle_blocks_slice*)calloc((size_t)threads, sizeof(oracle_blocks_slice));
+    pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    size_t per = (nblocks + (size_t)threads - 1) / (size_t)threads;
+    uint32_t sn = *samplenum;
+    for (int t = 0; t < threads; t++) {
+        size_t b0 = (size_t)t * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
+        if (b0 > nblocks) b0 = nblocks;
+        size_t k0 = b0 * blk, k1 = b1 * blk < nsamples ? b1 * blk : nsamples;
+        if (k0 > nsamples) k0 = nsamples;
+        sl[t] = (oracle_blocks_slice){in + k0 * ibps, out + k0 * obps, (k1 - k0) * ibps, intype, outtype, shifts + b0, nshifts - b0,
+                                      samplerate, sn, 0};
+        for (size_t b = b0; b < b1; b++) {   /* carry the state block by block, as the reference does */
+            size_t n = (b + 1) * blk <= nsamples ? blk : nsamples - b * blk;
+            sn = oracle_samplenum_advance(sn, shifts[b], samplerate, n);
+        }
+    }
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 1; t < threads; t++) pthread_create(&th[t], NULL, oracle_blocks_run, &sl[t]);
+    oracle_blocks_run(&sl[0]);
+    for (int t = 1; t < threads; t++) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    long bad = 0;
+    for (int t = 0; t < threads; t++) bad |= sl[t].rc < 0;
+    free(sl);
+    free(th);
+    if (bad) return -1.0;
+    *samplenum = sn;
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 

@@ -41,6 +41,7 @@ class Oracle:
         L.oracle_doppler_hz.restype = ctypes.c_double
         L.oracle_doppler_hz.argtypes = [ctypes.c_double, ctypes.c_uint32]
         L.oracle_bench_const.restype = ctypes.c_double
+        L.oracle_bench_blocks.restype = ctypes.c_double
         L.oracle_theta.restype = ctypes.c_float
         L.oracle_theta.argtypes = [ctypes.c_float, ctypes.c_uint32, ctypes.c_uint32]
         L.oracle_libc_version.restype = ctypes.c_char_p
@@ -177,6 +178,29 @@ class Oracle:
         t = self.lib.oracle_bench_const(_p(a), ctypes.c_size_t(nsamples), intype, outtype, ctypes.c_float(shift_hz),
                                         ctypes.c_uint32(samplerate), _p(out), ctypes.c_int(threads))
         return float(t), out
+
+
+    def bench_blocks(self, buf, nsamples, intype, outtype, shifts, samplerate, threads, samplenum=0):
+        """Threaded track-mode mix over a per-block schedule.  Returns (seconds, output bytes, final samplenum)."""
+        a = np.ascontiguousarray(buf.view(np.uint8).reshape(-1))
+        sh = np.ascontiguousarray(shifts, dtype=np.float32)
+        out = np.empty(nsamples * BPS[outtype], dtype=np.uint8)
+        sn = ctypes.c_uint32(samplenum)
+        t = self.lib.oracle_bench_blocks(_p(a), ctypes.c_size_t(nsamples), intype, outtype, _p(sh), ctypes.c_size_t(sh.size),
+                                         ctypes.c_uint32(samplerate), ctypes.byref(sn), _p(out), ctypes.c_int(threads))
+        if t < 0:
+            raise RuntimeError("oracle_bench_blocks: schedule shorter than the stream")
+        return float(t), out, sn.value
+
+    def mix_blocks_threads(self, buf, intype, outtype, shifts, samplerate, samplenum=0, threads=None):
+        """oracle.mix_blocks on all host cores (same bytes, same final samplenum)."""
+        import os
+        a = np.ascontiguousarray(np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf.view(np.uint8).reshape(-1))
+        if a.size % BPS[intype]:
+            return self.mix_blocks(a, intype, outtype, shifts, samplerate, samplenum)
+        threads = threads or len(os.sched_getaffinity(0))
+        _, out, sn = self.bench_blocks(a, a.size // BPS[intype], intype, outtype, shifts, samplerate, threads, samplenum)
+        return out, sn
 
 
 def same_bits_f32(a, b):

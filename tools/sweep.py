@@ -64,15 +64,7 @@ def run_case(mixer, stream, flush, label, intype, outtype, shift, fs, n, iters):
     return rec
 
 
-def overpass_shifts(fs, secs, ftx, tc, offset, intype, nsamples):
-    """Per-block shift schedule of the reference's replay driver for an analytic overpass."""
-    import numpy as np
-    from doppler_b200 import dsp
-    t = np.arange(secs + 2, dtype=np.float64)
-    v, d = 7500.0, 700e3
-    rr_km_s = v * v * (t - tc) / np.sqrt(d * d + (v * (t - tc)) ** 2) / 1000.0
-    table = np.array([dsp.doppler_hz(x, ftx) for x in rr_km_s])
-    return dsp.replay_schedule(table, offset, fs, intype, nsamples * BPS[intype])
+from tools.workloads import overpass_shifts  # noqa: E402,F401  (the BASELINE configs as code)
 
 
 def run_track_case(mixer, stream, label, intype, outtype, fs, shifts, n, seed, iters):

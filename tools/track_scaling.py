@@ -21,7 +21,7 @@ import torch.distributed as dist  # noqa: E402
 
 import doppler_b200  # noqa: E402
 from doppler_b200 import F32, slicing  # noqa: E402
-from sweep import overpass_shifts  # noqa: E402
+from tools.workloads import overpass_shifts  # noqa: E402
 from tests.oracle_lib import Oracle, same_bits_f32  # noqa: E402
 
 
