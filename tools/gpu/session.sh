@@ -28,8 +28,8 @@ for step in "$@"; do
     test)
       timeout 2700 python -m pytest ${TESTS:-tests} -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -6 $OUT/pytest_gpu.log ;;
     bench)
-      /usr/bin/time -v -o $OUT/bench.time timeout 1200 python bench.py $BENCH_ARGS > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
-      grep -E "Elapsed" $OUT/bench.time; cut -c1-400 $OUT/bench.json; tail -3 $OUT/bench.err ;;
+      t0=$SECONDS; timeout 1200 python bench.py $BENCH_ARGS > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$? wall=$((SECONDS - t0)) s"
+      cut -c1-400 $OUT/bench.json; tail -3 $OUT/bench.err ;;
     benchref)
       timeout 900 python bench.py --impl reference > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "benchref rc=$?"; cut -c1-300 $OUT/bench_ref.json ;;
     launches)
