@@ -26,6 +26,7 @@ SIGNATURES = {
     "doppler_b200_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
     "doppler_b200_libm_compatible": (ctypes.c_int, []),
     "doppler_b200_libm_mismatches": (ctypes.c_uint32, [ctypes.c_void_p]),
+    "doppler_b200_tune": (ctypes.c_int, [c_ctx, ctypes.c_int, ctypes.c_uint64]),
     "doppler_b200_launch_count": (ctypes.c_uint64, [c_ctx]),
     "doppler_b200_convert_iqi16_to_complex": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "doppler_b200_convert_iqf32_to_complex": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),

@@ -68,6 +68,8 @@ constexpr size_t kArenaEntries = 4ull << 20;         // 32 MiB of (cos, sin) pai
 constexpr uint32_t kSmemTabMaxEntries = 4096;        // 32 KiB of shared memory per CTA at most
 constexpr size_t kHostChunkBytes = 32ull << 20;      // host-path pipeline chunk (input side)
 constexpr int kSlots = 3;
+constexpr uint32_t kSmallMaxSamples = 4u << 20;      // launches up to this size take the latency-shaped kernel (mix_small_kernel); tools/tune
+constexpr size_t kTinyHostBytes = 128u << 10;        // host-buffer calls up to this much input run zero-copy over mapped pinned memory
 constexpr int kMetaSlots = 8;                        // pinned staging slots for launch metadata
 
 thread_local std::string g_create_error;   // create() errors, read back by the calling thread through last_error(NULL)
@@ -118,6 +120,13 @@ struct doppler_b200_ctx {
     cudaStream_t meta_stream = nullptr;   // metadata uploads run here, beside the previous launch's kernel
     std::string err;
     uint64_t launches = 0;
+    uint32_t small_max = kSmallMaxSamples;
+    size_t tiny_host_bytes = kTinyHostBytes;
+    // zero-copy per-block host path: completion flag in mapped host memory + CTA counter on the device
+    uint32_t* done_flag = nullptr;      // host (pinned)
+    uint32_t* done_flag_dev = nullptr;  // its device alias
+    uint32_t* done_counter = nullptr;   // device
+    uint32_t done_token = 0;
 };
 
 namespace {
@@ -444,8 +453,17 @@ long tiles_trace(const std::vector<DevPiece>& dev, uint32_t nsamp, uint32_t npip
 }
 
 // Enqueues the mixer over device buffers for a list of constant-shift runs.
+using SmallKernel = void (*)(const MixArgs, const dmix::SmallDone);
+SmallKernel small_kernel_for(int in, int out)
+{
+    static const SmallKernel k[2][2] = {{dmix::mix_small_kernel<0, 0>, dmix::mix_small_kernel<0, 1>},
+                                        {dmix::mix_small_kernel<1, 0>, dmix::mix_small_kernel<1, 1>}};
+    return k[in][out];
+}
+
+// `done` (optional): have the last CTA of a small launch raise a flag in host memory (zero-copy per-block path).
 int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t nsamples, int intype, int outtype,
-               const std::vector<dplan::Run>& runs, uint32_t* samplenum, cudaStream_t s)
+               const std::vector<dplan::Run>& runs, uint32_t* samplenum, cudaStream_t s, const dmix::SmallDone* done = nullptr)
 {
     if (nsamples == 0) return DOPPLER_B200_OK;
     std::vector<dplan::Piece> pieces;
@@ -489,18 +507,21 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         }
 
         const uint32_t nsamp = (uint32_t)(l1 - l0);
+        const bool small = done != nullptr || nsamp <= ctx->small_max;   // latency-shaped kernel: no segments, no shared-memory table
         std::vector<DevSeg> segs;
-        const uint32_t tail_begin = build_segments(dev, nsamp, shapes.seg.tile_samples, shapes.seg.gran,
-                                                   (uint32_t)ctx->sm_count * (uint32_t)shapes.seg.warps, &segs);
+        uint32_t tail_begin = nsamp;
+        if (!small)
+            tail_begin = build_segments(dev, nsamp, shapes.seg.tile_samples, shapes.seg.gran,
+                                        (uint32_t)ctx->sm_count * (uint32_t)shapes.seg.warps, &segs);
         // no COLUMN segment: the whole launch is one GRID segment and takes the lean loop
-        const bool grid_only = segs.size() <= 1 && (segs.empty() || segs[0].rows == 0);
+        const bool grid_only = small || (segs.size() <= 1 && (segs.empty() || segs[0].rows == 0));
         uint64_t tableless = 0;
         for (size_t i = 0; i < dev.size(); i++) tableless += dev[i].tab == dmix::kNoTab ? dev_len[i] : 0;
         const KernShape& shape = !grid_only ? shapes.seg : 2 * tableless > nsamp ? shapes.direct : shapes.grid;
         // one table per launch is staged in shared memory: the eligible piece covering most samples
         uint32_t smem_piece = dmix::kNoPiece;
         uint64_t smem_piece_len = 0;
-        for (size_t i = 0; i < dev.size(); i++)
+        for (size_t i = 0; !small && i < dev.size(); i++)
             if (dev[i].tab != dmix::kNoTab && dev[i].period <= shape.smem_tab_entries && dev_len[i] > smem_piece_len) {
                 smem_piece = (uint32_t)i;
                 smem_piece_len = dev_len[i];
@@ -532,7 +553,7 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         for (size_t i = 0; !up_segs && i < segs.size(); i++) a.inl_segs[i] = segs[i];
         char* d_meta = nullptr;
         MetaSlot* meta_slot = nullptr;
-        if (!grid_only || up_pieces) {
+        if (!grid_only || up_pieces) {   // (a small launch uploads only a long piece list)
             const std::vector<uint32_t> index = up_segs ? build_seg_index(segs) : std::vector<uint32_t>();
             const size_t off_pieces = 16, off_segs = off_pieces + (up_pieces ? dev.size() * sizeof(DevPiece) : 0);
             const size_t off_index = off_segs + (up_segs ? segs.size() * sizeof(DevSeg) : 0);
@@ -572,7 +593,14 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
                 a.seg_index = reinterpret_cast<const uint32_t*>(d_meta + off_index);
             }
         }
-        shape.kern<<<grid, shape.warps * 32, smem, s>>>(a);
+        if (small) {
+            const uint32_t groups = nsamp / (uint32_t)dmix::group_samples(intype, outtype);
+            const uint32_t ctas = std::max<uint32_t>(1, std::min<uint32_t>((groups + dmix::kSmallThreads - 1) / dmix::kSmallThreads,
+                                                                           (uint32_t)ctx->sm_count * 8u));
+            small_kernel_for(intype, outtype)<<<ctas, dmix::kSmallThreads, 0, s>>>(a, done ? *done : dmix::SmallDone{nullptr, nullptr, 0});
+        } else {
+            shape.kern<<<grid, shape.warps * 32, smem, s>>>(a);
+        }
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
         if (meta_slot) {
@@ -670,6 +698,81 @@ int retire_slot(doppler_b200_ctx* ctx, Slot& sl)
     return DOPPLER_B200_OK;
 }
 
+// Device-usable alias of a pinned host pointer (identical under unified addressing; asked for, not assumed).
+int device_alias(doppler_b200_ctx* ctx, const void* host, void** dev)
+{
+    CUDA_TRY(ctx, cudaHostGetDevicePointer(dev, const_cast<void*>(host), 0));
+    return DOPPLER_B200_OK;
+}
+
+int tiny_host_call(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int intype, int outtype, const float* shifts,
+                   size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint32_t* samplenum, void* out, bool in_pinned,
+                   bool out_pinned)
+{
+    const size_t ibps = bytes_per_sample(intype), obps = bytes_per_sample(outtype);
+    Slot& sl = ctx->slots[0];
+    int rc = retire_slot(ctx, sl);
+    if (rc) return rc;
+    rc = ensure_slot(ctx, sl, ctx->tiny_host_bytes, ctx->tiny_host_bytes * 2);
+    if (rc) return rc;
+    if (!ctx->done_flag) {
+        CUDA_TRY(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->done_flag), 64, cudaHostAllocMapped));
+        *ctx->done_flag = 0;
+        void* alias = nullptr;
+        rc = device_alias(ctx, ctx->done_flag, &alias);
+        if (rc) return rc;
+        ctx->done_flag_dev = static_cast<uint32_t*>(alias);
+        CUDA_TRY(ctx, cudaMalloc(&ctx->done_counter, 4));
+        CUDA_TRY(ctx, cudaMemset(ctx->done_counter, 0, 4));
+    }
+    // the caller's buffers serve directly when they are pinned, mapped and 16-byte aligned; otherwise the slot's staging does
+    void *src_dev = nullptr, *dst_dev = nullptr;
+    auto alias_ok = [&](const void* host, void** dev) {
+        if (cudaHostGetDevicePointer(dev, const_cast<void*>(host), 0) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return ((uintptr_t)*dev & 15) == 0;
+    };
+    if (!(in_pinned && alias_ok(in, &src_dev))) {
+        memcpy(sl.h_in, in, nsamples * ibps);
+        if ((rc = device_alias(ctx, sl.h_in, &src_dev))) return rc;
+    }
+    void* dst = out;
+    if (!(out_pinned && alias_ok(out, &dst_dev))) {
+        dst = sl.h_out;
+        if ((rc = device_alias(ctx, dst, &dst_dev))) return rc;
+    }
+    std::vector<dplan::Run> runs;
+    if (nblocks <= 1 || block_samples == 0)
+        runs.push_back(dplan::Run{nsamples, dplan::ratio(shifts[0], samplerate)});
+    else
+        runs = dplan::runs_from_blocks(shifts, nblocks, block_samples, samplerate, nsamples);
+    const uint32_t token = ++ctx->done_token ? ctx->done_token : ++ctx->done_token;   // never 0
+    const dmix::SmallDone done{ctx->done_counter, ctx->done_flag_dev, token};
+    rc = launch_mix(ctx, src_dev, dst_dev, nsamples, intype, outtype, runs, samplenum, sl.stream, &done);
+    if (rc) return rc;
+    // spin on the flag (host memory, written by the kernel's last CTA after a system-wide fence); a launch that died never
+    // raises it, so the stream is consulted now and then
+    volatile uint32_t* flag = ctx->done_flag;
+    for (uint32_t spins = 0; *flag != token; spins++) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0xfffffu) == 0xfffffu) {
+            const cudaError_t q = cudaStreamQuery(sl.stream);
+            if (q == cudaSuccess) break;   // finished (the flag store is visible by now or the kernel did not run at all)
+            if (q != cudaErrorNotReady) return fail(ctx, DOPPLER_B200_ECUDA, "small launch failed: %s", cudaGetErrorString(q));
+        }
+    }
+    if (*flag != token) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(sl.stream));
+        if (*flag != token) return fail(ctx, DOPPLER_B200_ECUDA, "small launch finished without raising its completion flag");
+    }
+    if (dst != out) memcpy(out, dst, nsamples * obps);
+    return DOPPLER_B200_OK;
+}
+
 // After a failed host-path call: nothing may stay in flight into the caller's buffers, and no slot may keep a
 // pending copy-out into memory the caller is free to release once the call has returned.
 void abandon_slots(doppler_b200_ctx* ctx)
@@ -702,6 +805,16 @@ int mix_host_run(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int i
     if (block_samples && nblocks > 1) chunk = std::max<uint64_t>(block_samples, chunk / block_samples * block_samples);
     const bool in_pinned = is_pinned(in), out_pinned = is_pinned(out);
     uint32_t sn = *samplenum;
+    if (!copy_only && nsamples * ibps <= ctx->tiny_host_bytes) {
+        // The reference's own call granularity (one 8192-byte pump block per shift_frequency call, main.rs:49,70): two
+        // cudaMemcpyAsync + an event wait cost more than the work.  Zero-copy instead: the latency-shaped kernel reads the
+        // block from mapped pinned host memory and writes the result there, and the host waits on a flag the kernel's last
+        // CTA raises in host memory.
+        int rc = tiny_host_call(ctx, in, nsamples, intype, outtype, shifts, nblocks, block_samples, samplerate, &sn, out, in_pinned, out_pinned);
+        if (rc) return rc;
+        *samplenum = sn;
+        return DOPPLER_B200_OK;
+    }
     int c = 0;
     for (uint64_t k = 0; k < nsamples; k += chunk, c++) {
         const uint64_t n = std::min(chunk, nsamples - k);
@@ -811,6 +924,8 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     if (!ctx) return fail(nullptr, DOPPLER_B200_ENOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("DOPPLER_B200_SMALL_MAX")) ctx->small_max = (uint32_t)strtoul(e, nullptr, 10);   // tuning knobs (tools/tune)
+    if (const char* e = getenv("DOPPLER_B200_TINY_BYTES")) ctx->tiny_host_bytes = (size_t)strtoul(e, nullptr, 10);
     cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&ctx->meta_stream, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->tables_ready, cudaEventDisableTiming);
@@ -845,6 +960,8 @@ void doppler_b200_destroy(doppler_b200_ctx* ctx)
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->done_flag) cudaFreeHost(ctx->done_flag);
+    if (ctx->done_counter) cudaFree(ctx->done_counter);
     if (ctx->meta_stream) cudaStreamDestroy(ctx->meta_stream);
     for (MetaSlot& ms : ctx->meta) {
         if (ms.copied) cudaEventDestroy(ms.copied);
@@ -877,7 +994,7 @@ void doppler_b200_host_free(void* p)
 int doppler_b200_host_register(void* p, size_t bytes)
 {
     if (!p || bytes == 0) return DOPPLER_B200_EINVAL;
-    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
         cudaGetLastError();
         return DOPPLER_B200_ECUDA;
     }
@@ -895,6 +1012,24 @@ int doppler_b200_host_unregister(void* p)
 }
 
 uint64_t doppler_b200_launch_count(const doppler_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int doppler_b200_tune(doppler_b200_ctx* ctx, int knob, uint64_t value)
+{
+    if (!ctx) return DOPPLER_B200_EINVAL;
+    switch (knob) {
+    case DOPPLER_B200_TUNE_SMALL_MAX_SAMPLES:
+        ctx->small_max = (uint32_t)std::min<uint64_t>(value, kLaunchMaxSamples);
+        return DOPPLER_B200_OK;
+    case DOPPLER_B200_TUNE_TINY_HOST_BYTES:
+        if (value > (8u << 20)) return fail(ctx, DOPPLER_B200_EINVAL, "tiny host path is limited to 8 MiB");
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        abandon_slots(ctx);
+        ctx->tiny_host_bytes = (size_t)value;
+        return DOPPLER_B200_OK;
+    default:
+        return fail(ctx, DOPPLER_B200_EINVAL, "unknown tuning knob %d", knob);
+    }
+}
 
 int doppler_b200_synchronize(doppler_b200_ctx* ctx)
 {

@@ -1022,6 +1022,103 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_grid_kernel(const __grid_co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small launches.  One second of the reference's own operating point (rtl_fm at 1.024 Msps, README.md:53) is
+// 4 MB; one pump block (main.rs:49) is 8 KB.  At these sizes the persistent bulk-async kernels above spend their
+// time on start-up (200 KB shared-memory carve-out, table staging, CTA barrier, pipeline fill and drain: ~11 us
+// per launch, profiles/r01_sweep_final2.md) while HBM needs well under a microsecond.  This kernel is the
+// latency-shaped variant: grid sized to the input, no shared memory, one 16-byte group per thread per step
+// (LDG -> registers -> STG), the phasor table of a short period read through L1 (it is a few KB and stays there),
+// everything else evaluated per sample with the generic routine.  It also serves the per-block host path
+// zero-copy: `in` / `out` may be mapped pinned HOST memory, and `done` lets the host wait on a flag in its own
+// memory instead of a stream synchronisation.
+constexpr int kSmallThreads = 256;
+
+struct SmallDone {
+    uint32_t* counter;          // device: CTAs finished (returns to 0)
+    volatile uint32_t* flag;    // mapped host memory: receives `token` when every CTA's stores are visible system-wide
+    uint32_t token;
+};
+
+template <int IN, int OUT>
+__global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_constant__ MixArgs a, const SmallDone done)
+{
+    constexpr int G = group_samples(IN, OUT);
+    const uint32_t ngroups = a.nsamples / G;
+    const uint32_t stride = gridDim.x * kSmallThreads;
+    uint32_t pi = 0;
+    DevPiece p = get_piece(a, 0);
+    for (uint32_t g = blockIdx.x * kSmallThreads + threadIdx.x; g < ngroups; g += stride) {
+        const uint32_t k0 = g * G;
+        uint32_t w[4] = {0, 0, 0, 0};
+        if constexpr (IN == I16 && G == 4) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(a.in) + g);
+            w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+        } else if constexpr (IN == I16) {
+            const uint2 v = __ldcs(reinterpret_cast<const uint2*>(a.in) + g);
+            w[0] = v.x, w[1] = v.y;
+        } else {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(a.in) + g);
+            w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+        }
+        float2 smp[G], res[G];
+        if constexpr (IN == I16) {
+#pragma unroll
+            for (int i = 0; i < G; i++) smp[i] = ingest_i16(w[i]);
+        } else {
+            smp[0] = make_float2(__uint_as_float(w[0]), __uint_as_float(w[1]));
+            smp[1] = make_float2(__uint_as_float(w[2]), __uint_as_float(w[3]));
+        }
+        if (k0 >= p.k_end) {
+            pi = find_piece(a, pi, k0);
+            p = get_piece(a, pi);
+        }
+        if (k0 + G <= p.k_end && p.tab != kNoTab) {
+            // inside one tabled piece: entries j .. j+G-1 of its table (replicated kTabPad >= G-1 entries past the period)
+            const float2* tab = a.tables + p.tab + (piece_samplenum(p, k0 - p.k_begin) - 1u);
+#pragma unroll
+            for (int i = 0; i < G; i++) res[i] = cmul_unfused(smp[i], __ldg(tab + i));
+        } else {
+            uint32_t qi = pi;
+            DevPiece q = p;
+#pragma unroll
+            for (int i = 0; i < G; i++) {
+                const uint32_t k = k0 + (uint32_t)i;
+                if (k >= q.k_end) {
+                    qi = find_piece(a, qi, k);
+                    q = get_piece(a, qi);
+                }
+                res[i] = cmul_unfused(smp[i], phasor(q.r, piece_samplenum(q, k - q.k_begin)));
+            }
+        }
+        if constexpr (OUT == I16 && G == 4) {
+            __stcs(reinterpret_cast<uint4*>(a.out) + g, make_uint4(egress_i16(res[0]), egress_i16(res[1]), egress_i16(res[2]), egress_i16(res[3])));
+        } else if constexpr (OUT == I16) {
+            __stcs(reinterpret_cast<uint2*>(a.out) + g, make_uint2(egress_i16(res[0]), egress_i16(res[1])));
+        } else {
+            __stcs(reinterpret_cast<float4*>(a.out) + g, make_float4(res[0].x, res[0].y, res[1].x, res[1].y));
+        }
+    }
+    // ragged end (fewer samples than a group): one thread each
+    const uint32_t tail = ngroups * G + blockIdx.x * kSmallThreads + threadIdx.x;
+    if (tail < a.nsamples) {
+        const uint32_t qi = find_piece(a, 0, tail);
+        const DevPiece q = get_piece(a, qi);
+        store_sample<OUT>(a.out, tail, cmul_unfused(load_sample<IN>(a.in, tail), phasor(q.r, piece_samplenum(q, tail - q.k_begin))));
+    }
+    if (done.flag) {
+        __threadfence_system();   // this thread's stores (possibly into host memory) are visible before the flag can be
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(done.counter, 1u) == gridDim.x - 1u) {
+                *done.counter = 0u;
+                __threadfence_system();
+                *done.flag = done.token;
+            }
+        }
+    }
+}
+
 // Phasor table of one shift: entry j (0 <= j < period + kTabPad) = phasor(r, (j mod period) + 1).
 __global__ void __launch_bounds__(kThreads) build_phasor_table_kernel(float2* tab, float r, uint32_t period, uint32_t entries)
 {

@@ -66,6 +66,13 @@ class Mixer:
     def synchronize(self):
         self._check(self._lib.doppler_b200_synchronize(self._ctx))
 
+    def tune(self, small_max_samples=None, tiny_host_bytes=None):
+        """Thresholds between code paths (doppler_b200_tune); results are identical on every path."""
+        if small_max_samples is not None:
+            self._check(self._lib.doppler_b200_tune(self._ctx, 1, int(small_max_samples)))
+        if tiny_host_bytes is not None:
+            self._check(self._lib.doppler_b200_tune(self._ctx, 2, int(tiny_host_bytes)))
+
     # -- reference functions -------------------------------------------------------------
     def convert_iqi16_to_complex(self, inbuf):
         """dsp.rs:85-99."""

@@ -95,6 +95,15 @@ int doppler_b200_host_unregister(void* p);
 /* Number of kernel launches issued by this context so far (mixer + table builders). */
 uint64_t doppler_b200_launch_count(const doppler_b200_ctx* ctx);
 
+/* Thresholds between the library's code paths (results are identical on every path; tests force each path,
+ * tools/latency.py tunes them).  SMALL_MAX_SAMPLES: launches up to this many samples take the latency-shaped
+ * kernel instead of the persistent bulk-async ones (0 = never).  TINY_HOST_BYTES: host-buffer calls with up to
+ * this much input run zero-copy over mapped pinned memory with a completion flag (0 = never; the reference calls
+ * its mixer once per 8192-byte block, main.rs:49,70). */
+#define DOPPLER_B200_TUNE_SMALL_MAX_SAMPLES 1
+#define DOPPLER_B200_TUNE_TINY_HOST_BYTES 2
+int doppler_b200_tune(doppler_b200_ctx* ctx, int knob, uint64_t value);
+
 /* ---- the reference's inner boundary, one to one (host buffers) --------------------------- */
 
 /* dsp::convert_iqi16_to_complex, src/dsp.rs:85-99.  out receives len/4 complex f32 samples

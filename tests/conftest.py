@@ -52,9 +52,14 @@ def oracle():
     return oracle_lib.Oracle()
 
 
-@pytest.fixture(scope="session")
-def mixer():
+@pytest.fixture(scope="session", params=["default", "bulk-async kernels only"])
+def mixer(request):
+    """The suite runs twice: with the product's thresholds (short inputs take the latency-shaped small kernel and the
+    zero-copy host path) and with both disabled, so that every input -- however short or ragged -- also goes through
+    the persistent bulk-async kernels and the staged host pipeline."""
     import doppler_b200
     m = doppler_b200.Mixer(0)
+    if request.param != "default":
+        m.tune(small_max_samples=0, tiny_host_bytes=0)
     yield m
     m.close()

@@ -355,3 +355,52 @@ def test_degenerate_ratios(oracle, mixer, shift, fs):
             want, sn_ref = oracle.mix(buf, intype, outtype, shift, fs)
             assert sn == sn_ref
             check(oracle, got, want, outtype)
+
+
+@pytest.mark.parametrize("intype,outtype", TYPE_PAIRS)
+def test_small_kernel_and_zero_copy_path_match_oracle(oracle, intype, outtype):
+    """The latency-shaped small kernel (device launches up to SMALL_MAX_SAMPLES) and the zero-copy per-block host path
+    (calls up to TINY_HOST_BYTES), forced on for every size here, including pieces that straddle groups, ragged ends,
+    pinned caller buffers at odd offsets and a per-block schedule."""
+    import ctypes
+    from doppler_b200 import _lib
+    lib = _lib.load()
+    m = doppler_b200.Mixer(0)
+    m.tune(small_max_samples=1 << 30, tiny_host_bytes=8 << 20)
+    rng = np.random.default_rng(31)
+    try:
+        for shift, fs in SHIFTS[:5] + [(1.0, 2_000_000_000)]:
+            for n in (1, 2, 3, 5, 2048, 2049, 30_001, 262_147):
+                buf = make_input(rng, n, intype)
+                got, sn = m.mix(buf, intype, outtype, shift, fs, samplenum=11)
+                want, sn_ref = oracle.mix(buf, intype, outtype, shift, fs, samplenum=11)
+                assert sn == sn_ref
+                check(oracle, got, want, outtype)
+        # one shift per 8192-byte block inside one tiny call
+        bs = BUFFER_SIZE // BPS[intype]
+        n = 9 * bs + 17
+        shifts = rng.uniform(-12000, 12000, 10).astype(np.float32)
+        buf = make_input(rng, n, intype)
+        got, sn = m.mix_blocks(buf, intype, outtype, shifts, 1_024_000)
+        want, sn_ref = oracle.mix_blocks(buf, intype, outtype, shifts, 1_024_000)
+        assert sn == sn_ref
+        check(oracle, got, want, outtype)
+        # pinned caller buffers: used in place when 16-byte aligned, staged when not
+        nb = 4096 * BPS[intype]
+        hin, hout = lib.doppler_b200_host_alloc(nb + 64), lib.doppler_b200_host_alloc(2 * nb + 64)
+        for off in (0, 8, 16):
+            src = np.ctypeslib.as_array(ctypes.cast(hin + off, ctypes.POINTER(ctypes.c_uint8)), shape=(nb,))
+            src[:] = make_input(rng, 4096, intype)
+            ob = 4096 * BPS[outtype]
+            dst = np.ctypeslib.as_array(ctypes.cast(hout + off, ctypes.POINTER(ctypes.c_uint8)), shape=(ob,))
+            snc, gotc = ctypes.c_uint32(0), ctypes.c_size_t(0)
+            rc = lib.doppler_b200_mix(m._ctx, hin + off, nb, intype, outtype, ctypes.c_float(7321.7), 1_024_000, ctypes.byref(snc), hout + off, ob,
+                                      ctypes.byref(gotc))
+            assert rc == 0 and gotc.value == ob
+            want, sn_ref = oracle.mix(src.copy(), intype, outtype, 7321.7, 1_024_000)
+            assert snc.value == sn_ref
+            check(oracle, dst.copy(), want, outtype)
+        lib.doppler_b200_host_free(hin)
+        lib.doppler_b200_host_free(hout)
+    finally:
+        m.close()
