@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -69,7 +70,8 @@ constexpr uint32_t kSmemTabMaxEntries = 4096;        // 32 KiB of shared memory 
 constexpr size_t kHostChunkBytes = 32ull << 20;      // host-path pipeline chunk (input side)
 constexpr int kSlots = 3;
 constexpr uint32_t kSmallMaxSamples = 4u << 20;      // launches up to this size take the latency-shaped kernel (mix_small_kernel); tools/tune
-constexpr size_t kTinyHostBytes = 128u << 10;        // host-buffer calls up to this much input run zero-copy over mapped pinned memory
+constexpr size_t kTinyHostBytes = 128u << 10;
+constexpr size_t kTinyStageBytes = 32u << 10;        // ... and up to this much is staged by memcpy without querying the caller's pointers        // host-buffer calls up to this much input run zero-copy over mapped pinned memory
 constexpr int kMetaSlots = 8;                        // pinned staging slots for launch metadata
 
 thread_local std::string g_create_error;   // create() errors, read back by the calling thread through last_error(NULL)
@@ -95,6 +97,8 @@ struct Slot {
     void* d_out = nullptr;
     void* h_in = nullptr;    // pinned staging
     void* h_out = nullptr;
+    void* h_in_dev = nullptr;   // device aliases of the staging buffers (zero-copy tiny path)
+    void* h_out_dev = nullptr;
     size_t in_cap = 0, out_cap = 0;
     // pending copy-out of a staged result
     void* user_out = nullptr;
@@ -114,6 +118,7 @@ struct doppler_b200_ctx {
     std::unordered_map<uint32_t, TableRef> tables;   // key: bits of r
     cudaEvent_t tables_ready = nullptr;
     bool tables_event_valid = false;
+    cudaStream_t tables_stream = nullptr;   // the stream the latest table build (and tables_ready) was enqueued on
     Slot slots[kSlots];
     MetaSlot meta[kMetaSlots];   // pinned staging for launch metadata (pieces, segments, work-unit counter)
     uint32_t meta_next = 0;
@@ -127,6 +132,9 @@ struct doppler_b200_ctx {
     uint32_t* done_flag_dev = nullptr;  // its device alias
     uint32_t* done_counter = nullptr;   // device
     uint32_t done_token = 0;
+    // DOPPLER_B200_TRACE=1: phase clock of the tiny host path (ns totals: staging in, plan + launch, wait for the flag, copy out)
+    bool trace = false;
+    uint64_t tiny_calls = 0, tiny_ns[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -166,6 +174,7 @@ struct KernShape {
     uint32_t fixed_smem;
     uint32_t (*table_bytes)(uint32_t period);
     uint32_t smem_tab_entries;   // longest period whose table this kernel stages in shared memory
+    uint32_t scratch_smem;       // per-CTA plateau scratch (direct-evaluation shape of the lean kernel), part of fixed_smem
 };
 // Per (intype, outtype): the lean loop for a launch that is one GRID segment (const mode), and the
 // segmented loop (GRID + COLUMN segments) with its own, larger tile.
@@ -185,18 +194,19 @@ constexpr uint32_t smem_tab_capacity(uint32_t fixed_smem, uint32_t row_samples)
     return fit < kSmemTabMaxEntries ? fit : kSmemTabMaxEntries;
 }
 
-template <int IN, int OUT, int WARPS, int S, int U, bool SEG>
+template <int IN, int OUT, int WARPS, int S, int U, bool SEG, bool PLATEAU = false>
 KernShape make_shape()
 {
     using C = dmix::StreamCfg<IN, OUT, WARPS, S, U>;
-    constexpr uint32_t fixed = SEG ? (uint32_t)C::kFixedSmem : (uint32_t)C::kGridSmem;
+    constexpr uint32_t scratch = PLATEAU ? (uint32_t)(WARPS * C::kPlateauBytes) : 0u;
+    constexpr uint32_t fixed = (SEG ? (uint32_t)C::kFixedSmem : (uint32_t)C::kGridSmem) + scratch;
     MixKernel kern;
     if constexpr (SEG)   // only the kernel this shape is for gets instantiated
         kern = dmix::mix_stream_kernel<IN, OUT, WARPS, S, U>;
     else
         kern = dmix::mix_grid_kernel<IN, OUT, WARPS, S, U>;
     return KernShape{kern, WARPS, (uint32_t)C::kTileSamples, (uint32_t)C::kRow, (uint32_t)C::kGran, fixed, &C::table_bytes,
-                     smem_tab_capacity(fixed, (uint32_t)C::kRow)};
+                     smem_tab_capacity(fixed, (uint32_t)C::kRow), scratch};
 }
 
 // (WARPS, S, U) of the segmented kernel per type pair; the host walk of the work decomposition
@@ -213,10 +223,10 @@ const StreamShape& shape_for(int in, int out)
     // isolated launches prefer (24,2,2) for f32->i16, r01_tune_stream_smemtab_fmul2.jsonl).
     // direct shapes: profiles/r01_tune_direct_linear.jsonl
     static const StreamShape shapes[2][2] = {
-        {{make_shape<0, 0, 20, 2, 2, false>(), make_shape<0, 0, SEG_I16I16, true>(), make_shape<0, 0, 12, 2, 6, false>()},
-         {make_shape<0, 1, 20, 3, 2, false>(), make_shape<0, 1, SEG_I16F32, true>(), make_shape<0, 1, 16, 2, 4, false>()}},
-        {{make_shape<1, 0, 16, 2, 3, false>(), make_shape<1, 0, SEG_F32I16, true>(), make_shape<1, 0, 16, 2, 6, false>()},
-         {make_shape<1, 1, 16, 2, 2, false>(), make_shape<1, 1, SEG_F32F32, true>(), make_shape<1, 1, 16, 2, 2, false>()}},
+        {{make_shape<0, 0, 20, 2, 2, false>(), make_shape<0, 0, SEG_I16I16, true>(), make_shape<0, 0, 12, 2, 6, false, true>()},
+         {make_shape<0, 1, 20, 3, 2, false>(), make_shape<0, 1, SEG_I16F32, true>(), make_shape<0, 1, 16, 2, 4, false, true>()}},
+        {{make_shape<1, 0, 16, 2, 3, false>(), make_shape<1, 0, SEG_F32I16, true>(), make_shape<1, 0, 16, 2, 6, false, true>()},
+         {make_shape<1, 1, 16, 2, 2, false>(), make_shape<1, 1, SEG_F32F32, true>(), make_shape<1, 1, 16, 2, 2, false, true>()}},
     };
     return shapes[in][out];
 }
@@ -266,6 +276,7 @@ int get_table(doppler_b200_ctx* ctx, float r, uint32_t period, uint64_t piece_le
     ctx->launches++;
     CUDA_TRY(ctx, cudaEventRecord(ctx->tables_ready, s));
     ctx->tables_event_valid = true;
+    ctx->tables_stream = s;
     ctx->arena_used += (entries + 1) & ~(size_t)1;   // keep 16-byte alignment of table starts
     ctx->tables[key] = TableRef{off, period};
     *off_out = off;
@@ -454,11 +465,14 @@ long tiles_trace(const std::vector<DevPiece>& dev, uint32_t nsamp, uint32_t npip
 
 // Enqueues the mixer over device buffers for a list of constant-shift runs.
 using SmallKernel = void (*)(const MixArgs, const dmix::SmallDone);
-SmallKernel small_kernel_for(int in, int out)
+constexpr int kSmallV = 4;   // groups per thread per step in the throughput flavour of the small kernel
+SmallKernel small_kernel_for(int in, int out, bool wide)
 {
-    static const SmallKernel k[2][2] = {{dmix::mix_small_kernel<0, 0>, dmix::mix_small_kernel<0, 1>},
-                                        {dmix::mix_small_kernel<1, 0>, dmix::mix_small_kernel<1, 1>}};
-    return k[in][out];
+    static const SmallKernel k1[2][2] = {{dmix::mix_small_kernel<0, 0, 1>, dmix::mix_small_kernel<0, 1, 1>},
+                                         {dmix::mix_small_kernel<1, 0, 1>, dmix::mix_small_kernel<1, 1, 1>}};
+    static const SmallKernel kv[2][2] = {{dmix::mix_small_kernel<0, 0, kSmallV>, dmix::mix_small_kernel<0, 1, kSmallV>},
+                                         {dmix::mix_small_kernel<1, 0, kSmallV>, dmix::mix_small_kernel<1, 1, kSmallV>}};
+    return wide ? kv[in][out] : k1[in][out];
 }
 
 // `done` (optional): have the last CTA of a small launch raise a flag in host memory (zero-copy per-block path).
@@ -476,7 +490,8 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
     const uint64_t lcm_tile = std::lcm<uint64_t>(std::lcm<uint64_t>(shapes.grid.tile_samples, shapes.seg.tile_samples), shapes.direct.tile_samples);
     const uint64_t launch_max = kLaunchMaxSamples / lcm_tile * lcm_tile;
 
-    if (ctx->tables_event_valid) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->tables_ready, 0));
+    // table builds are ordered before this launch: by stream order when they were enqueued on `s` itself, through the event otherwise
+    if (ctx->tables_event_valid && s != ctx->tables_stream) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->tables_ready, 0));
 
     for (uint64_t l0 = 0; l0 < nsamples; l0 += launch_max) {
         const uint64_t l1 = std::min(nsamples, l0 + launch_max);
@@ -538,6 +553,7 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         a.nunits = segs.empty() ? 0 : segs.back().unit_end;
         a.tail_begin = tail_begin;
         a.smem_piece = smem_piece;
+        a.plateau_scratch = shape.scratch_smem != 0;
         // persistent: one CTA per SM, every warp an independent pipeline over interleaved work units
         if (grid_only) a.nunits = nsamp / shape.tile_samples;   // whole tiles; the lean loop mixes the ragged end itself
         const uint32_t want = (a.nunits + shape.warps - 1) / shape.warps;
@@ -594,10 +610,14 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
             }
         }
         if (small) {
-            const uint32_t groups = nsamp / (uint32_t)dmix::group_samples(intype, outtype);
-            const uint32_t ctas = std::max<uint32_t>(1, std::min<uint32_t>((groups + dmix::kSmallThreads - 1) / dmix::kSmallThreads,
-                                                                           (uint32_t)ctx->sm_count * 8u));
-            small_kernel_for(intype, outtype)<<<ctas, dmix::kSmallThreads, 0, s>>>(a, done ? *done : dmix::SmallDone{nullptr, nullptr, 0});
+            // one group per thread while that still fills the chip once over (latency), kSmallV per thread beyond (bytes in
+            // flight); a flagged zero-copy launch of up to 1024 groups is ONE CTA: no cross-CTA counter before the flag
+            const uint32_t groups = std::max<uint32_t>(1, nsamp / (uint32_t)dmix::group_samples(intype, outtype));
+            const bool one_cta = done != nullptr && groups <= (uint32_t)dmix::kSmallThreads * kSmallV;
+            const bool wide = one_cta || groups > (uint32_t)ctx->sm_count * 8u * dmix::kSmallThreads;
+            const uint32_t per_cta = (uint32_t)dmix::kSmallThreads * (wide ? kSmallV : 1);
+            const uint32_t ctas = one_cta ? 1u : std::min<uint32_t>((groups + per_cta - 1) / per_cta, (uint32_t)ctx->sm_count * 32u);
+            small_kernel_for(intype, outtype, wide)<<<ctas, dmix::kSmallThreads, 0, s>>>(a, done ? *done : dmix::SmallDone{nullptr, nullptr, 0});
         } else {
             shape.kern<<<grid, shape.warps * 32, smem, s>>>(a);
         }
@@ -642,6 +662,7 @@ int ensure_slot(doppler_b200_ctx* ctx, Slot& sl, size_t in_bytes, size_t out_byt
         sl.in_cap = 0;
         CUDA_TRY(ctx, cudaMalloc(&sl.d_in, in_bytes));
         CUDA_TRY(ctx, cudaMallocHost(&sl.h_in, in_bytes));
+        CUDA_TRY(ctx, cudaHostGetDevicePointer(&sl.h_in_dev, sl.h_in, 0));
         sl.in_cap = in_bytes;
     }
     if (sl.out_cap < out_bytes) {
@@ -651,6 +672,7 @@ int ensure_slot(doppler_b200_ctx* ctx, Slot& sl, size_t in_bytes, size_t out_byt
         sl.out_cap = 0;
         CUDA_TRY(ctx, cudaMalloc(&sl.d_out, out_bytes));
         CUDA_TRY(ctx, cudaMallocHost(&sl.h_out, out_bytes));
+        CUDA_TRY(ctx, cudaHostGetDevicePointer(&sl.h_out_dev, sl.h_out, 0));
         sl.out_cap = out_bytes;
     }
     return DOPPLER_B200_OK;
@@ -706,8 +728,7 @@ int device_alias(doppler_b200_ctx* ctx, const void* host, void** dev)
 }
 
 int tiny_host_call(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int intype, int outtype, const float* shifts,
-                   size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint32_t* samplenum, void* out, bool in_pinned,
-                   bool out_pinned)
+                   size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint32_t* samplenum, void* out)
 {
     const size_t ibps = bytes_per_sample(intype), obps = bytes_per_sample(outtype);
     Slot& sl = ctx->slots[0];
@@ -725,24 +746,27 @@ int tiny_host_call(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int
         CUDA_TRY(ctx, cudaMalloc(&ctx->done_counter, 4));
         CUDA_TRY(ctx, cudaMemset(ctx->done_counter, 0, 4));
     }
-    // the caller's buffers serve directly when they are pinned, mapped and 16-byte aligned; otherwise the slot's staging does
-    void *src_dev = nullptr, *dst_dev = nullptr;
+    // Up to kTinyStageBytes the block is simply copied through the slot's pinned staging (an 8 KiB memcpy costs less than
+    // asking the driver what kind of memory the caller's pointers are); larger tiny calls use the caller's buffers in place
+    // when they are pinned, mapped and 16-byte aligned.
+    void *src_dev = sl.h_in_dev, *dst_dev = sl.h_out_dev;
+    void* dst = sl.h_out;
     auto alias_ok = [&](const void* host, void** dev) {
-        if (cudaHostGetDevicePointer(dev, const_cast<void*>(host), 0) != cudaSuccess) {
+        if (!is_pinned(host)) return false;
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, const_cast<void*>(host), 0) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
-        return ((uintptr_t)*dev & 15) == 0;
+        if ((uintptr_t)d & 15) return false;
+        *dev = d;
+        return true;
     };
-    if (!(in_pinned && alias_ok(in, &src_dev))) {
-        memcpy(sl.h_in, in, nsamples * ibps);
-        if ((rc = device_alias(ctx, sl.h_in, &src_dev))) return rc;
-    }
-    void* dst = out;
-    if (!(out_pinned && alias_ok(out, &dst_dev))) {
-        dst = sl.h_out;
-        if ((rc = device_alias(ctx, dst, &dst_dev))) return rc;
-    }
+    const auto t_0 = std::chrono::steady_clock::now();
+    const bool probe = nsamples * ibps > kTinyStageBytes;
+    if (!(probe && alias_ok(in, &src_dev))) memcpy(sl.h_in, in, nsamples * ibps);
+    if (probe && alias_ok(out, &dst_dev)) dst = out;
+    const auto t_1 = std::chrono::steady_clock::now();
     std::vector<dplan::Run> runs;
     if (nblocks <= 1 || block_samples == 0)
         runs.push_back(dplan::Run{nsamples, dplan::ratio(shifts[0], samplerate)});
@@ -752,6 +776,7 @@ int tiny_host_call(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int
     const dmix::SmallDone done{ctx->done_counter, ctx->done_flag_dev, token};
     rc = launch_mix(ctx, src_dev, dst_dev, nsamples, intype, outtype, runs, samplenum, sl.stream, &done);
     if (rc) return rc;
+    const auto t_2 = std::chrono::steady_clock::now();
     // spin on the flag (host memory, written by the kernel's last CTA after a system-wide fence); a launch that died never
     // raises it, so the stream is consulted now and then
     volatile uint32_t* flag = ctx->done_flag;
@@ -769,7 +794,15 @@ int tiny_host_call(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int
         CUDA_TRY(ctx, cudaStreamSynchronize(sl.stream));
         if (*flag != token) return fail(ctx, DOPPLER_B200_ECUDA, "small launch finished without raising its completion flag");
     }
+    if (ctx->tables_stream == sl.stream) ctx->tables_event_valid = false;   // everything enqueued on this stream has finished
+    const auto t_3 = std::chrono::steady_clock::now();
     if (dst != out) memcpy(out, dst, nsamples * obps);
+    if (ctx->trace) {
+        const auto t_4 = std::chrono::steady_clock::now();
+        auto ns = [](auto a, auto b) { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+        ctx->tiny_calls++;
+        ctx->tiny_ns[0] += ns(t_0, t_1), ctx->tiny_ns[1] += ns(t_1, t_2), ctx->tiny_ns[2] += ns(t_2, t_3), ctx->tiny_ns[3] += ns(t_3, t_4);
+    }
     return DOPPLER_B200_OK;
 }
 
@@ -803,18 +836,18 @@ int mix_host_run(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int i
     }();
     uint64_t chunk = chunk_bytes / ibps;
     if (block_samples && nblocks > 1) chunk = std::max<uint64_t>(block_samples, chunk / block_samples * block_samples);
-    const bool in_pinned = is_pinned(in), out_pinned = is_pinned(out);
     uint32_t sn = *samplenum;
     if (!copy_only && nsamples * ibps <= ctx->tiny_host_bytes) {
         // The reference's own call granularity (one 8192-byte pump block per shift_frequency call, main.rs:49,70): two
         // cudaMemcpyAsync + an event wait cost more than the work.  Zero-copy instead: the latency-shaped kernel reads the
         // block from mapped pinned host memory and writes the result there, and the host waits on a flag the kernel's last
         // CTA raises in host memory.
-        int rc = tiny_host_call(ctx, in, nsamples, intype, outtype, shifts, nblocks, block_samples, samplerate, &sn, out, in_pinned, out_pinned);
+        int rc = tiny_host_call(ctx, in, nsamples, intype, outtype, shifts, nblocks, block_samples, samplerate, &sn, out);
         if (rc) return rc;
         *samplenum = sn;
         return DOPPLER_B200_OK;
     }
+    const bool in_pinned = is_pinned(in), out_pinned = is_pinned(out);
     int c = 0;
     for (uint64_t k = 0; k < nsamples; k += chunk, c++) {
         const uint64_t n = std::min(chunk, nsamples - k);
@@ -924,6 +957,7 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     if (!ctx) return fail(nullptr, DOPPLER_B200_ENOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->trace = getenv("DOPPLER_B200_TRACE") != nullptr;
     if (const char* e = getenv("DOPPLER_B200_SMALL_MAX")) ctx->small_max = (uint32_t)strtoul(e, nullptr, 10);   // tuning knobs (tools/tune)
     if (const char* e = getenv("DOPPLER_B200_TINY_BYTES")) ctx->tiny_host_bytes = (size_t)strtoul(e, nullptr, 10);
     cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -949,6 +983,10 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
 void doppler_b200_destroy(doppler_b200_ctx* ctx)
 {
     if (!ctx) return;
+    if (ctx->trace && ctx->tiny_calls)
+        fprintf(stderr, "{\"tiny_host_calls\": %llu, \"ns_per_call\": {\"stage_in\": %.0f, \"plan_and_launch\": %.0f, \"wait_flag\": %.0f, \"copy_out\": %.0f}}\n",
+                (unsigned long long)ctx->tiny_calls, (double)ctx->tiny_ns[0] / ctx->tiny_calls, (double)ctx->tiny_ns[1] / ctx->tiny_calls,
+                (double)ctx->tiny_ns[2] / ctx->tiny_calls, (double)ctx->tiny_ns[3] / ctx->tiny_calls);
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (Slot& sl : ctx->slots) {

@@ -116,6 +116,7 @@ struct MixArgs {
     uint32_t nunits;          // work units over all segments
     uint32_t tail_begin;      // samples [tail_begin, nsamples): the sub-granule end of the buffer
     uint32_t smem_piece;      // streaming kernel: piece whose table is staged in shared memory, or kNoPiece
+    uint32_t plateau_scratch; // lean kernel: 1 when the launch carries a per-warp plateau scratch (direct-evaluation shape)
     DevPiece inl[kInlinePieces];
     DevSeg inl_segs[kInlineSegs];
 };
@@ -165,13 +166,15 @@ __device__ __forceinline__ float2 cmul_unfused(float2 smp, float2 ph)
     return make_float2(__fadd_rn(ac, nbd), __fadd_rn(ad, bc));
 }
 
-// i16 -> f32 of the low / high half of an IQ word without the slow-pipe I2F.S16 (measured ~4.5
-// issue cycles per warp against ~1.7 for LOP3 / FADD / I2FP, profiles/r01_pipes.jsonl):
-// low half by exponent bias, (2^23 + 2^15 + i) - (2^23 + 2^15), exact for every i16; high half by
-// arithmetic shift + I2FP.F32.S32.
+// i16 -> f32 of the low / high half of an IQ word without the slow-pipe I2F.S16 (measured ~4.5 issue cycles per warp
+// against ~1.7 for PRMT / SHF / I2FP, profiles/r01_pipes.jsonl): sign-extend in the integer pipe -- low half with one
+// byte permute whose upper two selectors replicate the sign of byte 1 (PRMT 0x9910), high half with an arithmetic
+// shift -- then I2FP.F32.S32.  Two instructions per component (the round-1 exponent-bias trick for the low half was three).
 __device__ __forceinline__ float i16_lo_f32(uint32_t w)
 {
-    return __fsub_rn(__uint_as_float((w & 0xffffu) ^ 0x4b008000u), 8421376.0f);
+    int v;
+    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(v) : "r"(w));   // {b0, b1, sign(b1), sign(b1)}: inline asm keeps ptxas from fusing into I2F.S16
+    return __int2float_rn(v);
 }
 __device__ __forceinline__ float i16_hi_f32(uint32_t w) { return __int2float_rn((int)w >> 16); }
 
@@ -338,6 +341,11 @@ struct StreamCfg {
     static constexpr int kWinBytes = G * kWinPlane * 8;            // per warp
     static constexpr int kFixedSmem = kBarBytes + WARPS * (kRing + kDescBytes + kWinBytes);   // mix_stream_kernel
     static constexpr int kGridSmem = kBarBytes + WARPS * kRing;                                // mix_grid_kernel (no descriptors / windows)
+    // PLATEAU scratch (direct evaluation above samplenum 2^24, where f32(n) takes one value per 2 .. 256 consecutive n):
+    // the distinct phasors of one tile, at most kTileSamples / 2 + 2 of them
+    static constexpr int kPlateauEntries = ((kTileSamples / 2 + 2 + 15) / 16) * 16;
+    static constexpr int kPlateauBytes = kPlateauEntries * 8;      // per warp; the segmented kernel reuses its COLUMN window instead
+    static_assert(G * kWinPlane >= kPlateauEntries, "the COLUMN window doubles as the plateau scratch");
     // shared-memory table: G planes of plane_len(entries) float2 each
     __host__ __device__ static constexpr uint32_t plane_len(uint32_t period) { return (period + kRow + G - 1) / G + 1; }
     __host__ __device__ static constexpr uint32_t table_bytes(uint32_t period) { return G * plane_len(period) * 8; }
@@ -513,9 +521,16 @@ __device__ __forceinline__ void stream_rows(const uint32_t (&raw)[C::U][4], unsi
 }
 
 // One full tile inside one table-less piece (linear, or periodic without a table): direct evaluation.
+//
+// PLATEAUS.  The reference forms theta from `samplenum as f32` (dsp.rs:121), and above 2^24 that conversion takes ONE
+// value for 2, 4, ... 256 consecutive samplenums (round to nearest even): a stream that never resets (tiny |r|) spends
+// almost all of its life there.  Inside one tile the distinct values are the floats between f32(n_first) and
+// f32(n_last) -- consecutive bit patterns, so value e is bits(f32(n_first)) + e and sample n uses entry
+// bits(f32(n)) - bits(f32(n_first)).  The warp evaluates each distinct phasor once into `scratch` (<= T/2 + 1
+// evaluations for T samples, T/256 + 1 near the top of the u32 range) and every sample looks its own up.
 template <typename C, int IN, int OUT>
 __device__ __forceinline__ void stream_tile_direct(const uint32_t (&raw)[C::U][4], unsigned char* out_s, const DevPiece& p,
-                                                   uint32_t k0, uint32_t lane)
+                                                   uint32_t k0, uint32_t lane, float2* scratch)
 {
     constexpr uint32_t kTile = C::kTileSamples;
     const uint32_t off0 = k0 - p.k_begin;
@@ -533,6 +548,30 @@ __device__ __forceinline__ void stream_tile_direct(const uint32_t (&raw)[C::U][4
     db_window_t dt;
     const int range = mono ? classify_tile(r, n0, n0 + (kTile - 1u), dt) : (int)kRangeGeneric;
     const uint32_t nl = n0 + lane * C::G;   // this lane's first samplenum in row 0
+    if (mono && scratch != nullptr && n0 >= (1u << 24)) {
+        const uint32_t b0 = __float_as_uint(__uint2float_rn(n0));
+        const uint32_t nvals = __float_as_uint(__uint2float_rn(n0 + (kTile - 1u))) - b0 + 1u;   // <= kTile / 2 + 1
+        auto theta_e = [&](uint32_t e) { return __fmul_rn(__uint_as_float(0xC0C90FDBu), __fmul_rn(r, __uint_as_float(b0 + e))); };
+        if (range == kRangeLarge) {
+            for (uint32_t e = lane; e < nvals; e += 32) scratch[e] = phasor_fast<kRangeLarge>(theta_e(e), dt);
+        } else if (range == kRangeMedium) {
+            for (uint32_t e = lane; e < nvals; e += 32) scratch[e] = phasor_fast<kRangeMedium>(theta_e(e), dt);
+        } else if (range == kRangeSmall) {
+            for (uint32_t e = lane; e < nvals; e += 32) scratch[e] = phasor_fast<kRangeSmall>(theta_e(e), dt);
+        } else if (range == kRangeTiny) {
+            for (uint32_t e = lane; e < nvals; e += 32) scratch[e] = phasor_fast<kRangeTiny>(theta_e(e), dt);
+        } else {
+#pragma unroll 1
+            for (uint32_t e = lane; e < nvals; e += 32) {
+                const db_sincos_t sc = db_sincosf_glibc(theta_e(e));
+                scratch[e] = make_float2(sc.c, sc.s);
+            }
+        }
+        __syncwarp();
+        // (the caller's __syncwarp before the tile's bulk store separates these reads from the next tile's writes)
+        stream_rows<C, IN, OUT>(raw, out_s, lane, [&](int i) { return scratch[__float_as_uint(__uint2float_rn(nl + (uint32_t)i)) - b0]; });
+        return;
+    }
     if (range == kRangeLarge) {
         stream_rows<C, IN, OUT>(raw, out_s, lane, [&](int i) { return phasor_fast<kRangeLarge>(theta_of(r, nl + (uint32_t)i), dt); });
     } else if (range == kRangeMedium) {
@@ -643,118 +682,198 @@ __device__ __forceinline__ void stream_tile_column(const uint32_t (&raw)[C::U][4
     }
 }
 
-// Lane 0's work iterator: expands work units into tiles.  On the device, units are claimed
-// kUnitChunk at a time from a global counter (a COLUMN unit costs 2-64 tiles plus a window evaluation,
-// a GRID unit kGridUnitTiles tiles: a static split left ~10 % of the SMs idle at the end of a track-mode launch);
-// the claim for the NEXT chunk is issued when a chunk starts, so its latency hides behind the
-// chunk's tiles.  On the host (doppler_b200_plan_tiles_trace) pipeline p walks chunks p, p + npipes, ...
-constexpr uint32_t kUnitChunk = 1;
+// Work units -> tiles.  Work units are claimed one at a time from a global counter (a COLUMN unit costs 2-64 tiles plus a
+// window evaluation, a GRID unit kGridUnitTiles tiles: a static split left ~10 % of the SMs idle at the end of a track-mode
+// launch).  Every tile of a unit is a CLOSED FORM of (segment, unit, tile index) -- unit_tile() below -- so nothing about the
+// expansion is sequential: on the device all 32 lanes of the warp expand the unit's tiles at once, lane t tile t (TileSrc),
+// and handing out the next tile is a ballot and a few shuffles instead of a scalar iterator run by lane 0 (round 1: ~55
+// issued instructions per tile with one active lane).  On the host (doppler_b200_plan_tiles_trace) TileIter walks the same
+// closed form tile by tile, pipeline p taking units p, p + npipes, ...
 constexpr uint32_t kGridUnitTiles = 8;   // a GRID work unit is this many consecutive tiles (comparable to a COLUMN unit)
 
+struct UnitPos {        // warp-uniform position of one work unit inside its segment
+    uint32_t ntiles;    // GRID: tiles of the unit; COLUMN: rows of the unit (rows whose column tile is empty are skipped)
+    uint32_t c;         // COLUMN: column tile
+    uint32_t j0;        // GRID: first tile of the unit within the segment; COLUMN: first row
+};
+
+template <typename C>
+__host__ __device__ __forceinline__ UnitPos unit_pos(const DevSeg& sg, uint32_t u)
+{
+    constexpr uint32_t T = C::kTileSamples;
+    const uint32_t v = u - sg.unit_begin;
+    UnitPos up;
+    if (sg.rows == 0) {
+        const uint32_t ntiles = (sg.k_end - sg.k_begin + T - 1) / T;
+        up.c = 0;
+        up.j0 = v * kGridUnitTiles;
+        up.ntiles = up.j0 + kGridUnitTiles < ntiles ? kGridUnitTiles : ntiles - up.j0;
+    } else {
+        const uint32_t g = (uint32_t)(((uint64_t)v * sg.ncols_magic) >> sg.ncols_shift);
+        up.c = v - g * sg.ncols;
+        up.j0 = g * sg.rows_per_unit;
+        up.ntiles = up.j0 + sg.rows_per_unit < sg.rows ? sg.rows_per_unit : sg.rows - up.j0;
+    }
+    return up;
+}
+
+// Tile t of the unit: k0 / nsamp / skip / info (row shift, kColFlag); nsamp == 0 when the row has no samples in this column.
+template <typename C>
+__host__ __device__ __forceinline__ void unit_tile(const DevSeg& sg, const UnitPos& up, uint32_t t, uint32_t& k0, uint32_t& nsamp,
+                                                   uint32_t& skip, uint32_t& info)
+{
+    constexpr uint32_t T = C::kTileSamples, GM = ~(uint32_t)(C::kGran - 1);
+    if (sg.rows == 0) {
+        const uint32_t start = sg.k_begin + (up.j0 + t) * T;
+        k0 = start;
+        nsamp = sg.k_end - start < T ? sg.k_end - start : T;
+        skip = 0;
+        info = 0;
+        return;
+    }
+    const uint32_t j = up.j0 + t;
+    const int32_t kj = (int32_t)sg.k0 + (int32_t)(j * sg.period);
+    const int32_t aj = kj & (int32_t)GM, aj1 = (kj + (int32_t)sg.period) & (int32_t)GM;
+    const int32_t start = aj + (int32_t)(up.c * T);
+    int32_t hi = start + (int32_t)T < aj1 ? start + (int32_t)T : aj1;   // the row's last column is short
+    if (hi > (int32_t)sg.k_end) hi = (int32_t)sg.k_end;                   // the segment's last row is partial
+    const int32_t lo = start > (int32_t)sg.k_begin ? start : (int32_t)sg.k_begin;   // so is its first
+    k0 = (uint32_t)start;
+    skip = lo < hi ? (uint32_t)(lo - start) : 0u;
+    nsamp = lo < hi ? (uint32_t)(hi - start) : 0u;
+    info = kColFlag | (uint32_t)(kj - aj);
+}
+
+// Host walk (tests): pipeline `pipe` of `npipes` takes units pipe, pipe + npipes, ... and expands each tile by tile.
 template <typename C>
 struct TileIter {
-    uint32_t u, uend, next_base, step, nunits;
-    uint32_t seg;
+    uint32_t u, step, nunits, seg, t;
     DevSeg sg;
-    uint32_t c, j, jend;
+    UnitPos up;
     bool first;
 
-    __host__ __device__ __forceinline__ uint32_t claim(const MixArgs& a)
+    __host__ void init(const MixArgs& a, uint32_t pipe, uint32_t npipes)
     {
-#if defined(__CUDA_ARCH__)
-        return atomicAdd(a.unit_counter, kUnitChunk);
-#else
-        (void)a;
-        const uint32_t b = next_base + step;   // host walk: static striding over chunks
-        return b;
-#endif
-    }
-
-    __host__ __device__ __forceinline__ void init(const MixArgs& a, uint32_t pipe, uint32_t npipes)
-    {
-        step = npipes * kUnitChunk;
+        step = npipes;
         nunits = a.nunits;
-        u = uend = 0;
-#if defined(__CUDA_ARCH__)
-        (void)pipe;
-        next_base = claim(a);
-#else
-        next_base = pipe * kUnitChunk;
-#endif
+        u = pipe;
         seg = 0;
         sg = get_seg(a, 0);
-        c = j = jend = 0;
+        up.ntiles = up.c = up.j0 = 0;
+        t = 0;
         first = false;
     }
 
-    __host__ __device__ __forceinline__ bool next(const MixArgs& a, TileDesc& d)
+    __host__ bool next(const MixArgs& a, TileDesc& d)
     {
-        constexpr uint32_t T = C::kTileSamples, GM = ~(uint32_t)(C::kGran - 1);
         for (;;) {
-            if (j < jend && sg.rows == 0) {   // tiles left in the current GRID unit
-                const uint32_t start = sg.k_begin + j * T;
-                j++;
-                d.k0 = start;
-                d.nsamp = sg.k_end - start < T ? sg.k_end - start : T;
+            if (t < up.ntiles) {
+                unit_tile<C>(sg, up, t++, d.k0, d.nsamp, d.skip, d.info);
+                if (d.nsamp == 0) continue;
                 d.seg = seg;
-                d.info = 0;
-                d.phase0 = sg.piece;
-                d.period = 0;
-                d.r = 0.0f;
-                d.skip = 0;
-                return true;
-            }
-            if (j < jend) {   // rows left in the current COLUMN unit
-                const int32_t kj = (int32_t)sg.k0 + (int32_t)(j * sg.period);
-                const int32_t aj = kj & (int32_t)GM, aj1 = (kj + (int32_t)sg.period) & (int32_t)GM;
-                const int32_t start = aj + (int32_t)(c * T);
-                j++;
-                int32_t hi = start + (int32_t)T < aj1 ? start + (int32_t)T : aj1;   // the row's last column is short
-                if (hi > (int32_t)sg.k_end) hi = (int32_t)sg.k_end;                   // the segment's last row is partial
-                const int32_t lo = start > (int32_t)sg.k_begin ? start : (int32_t)sg.k_begin;   // so is its first
-                if (lo >= hi) continue;
-                d.k0 = (uint32_t)start;
-                d.skip = (uint32_t)(lo - start);
-                d.nsamp = (uint32_t)(hi - start);
-                d.seg = seg;
-                d.info = kColFlag | (first ? kColFirst : 0u) | (uint32_t)(kj - aj);
-                d.phase0 = c * T;
-                d.period = sg.period;
-                d.r = sg.r;
+                d.phase0 = sg.rows ? up.c * (uint32_t)C::kTileSamples : sg.piece;
+                d.period = sg.rows ? sg.period : 0u;
+                d.r = sg.rows ? sg.r : 0.0f;
+                if (sg.rows && first) d.info |= kColFirst;
                 first = false;
                 return true;
             }
-            if (u >= uend) {   // chunk exhausted: take the one claimed earlier, claim the one after
-                if (next_base >= nunits) return false;
-                u = next_base;
-                uend = u + kUnitChunk < nunits ? u + kUnitChunk : nunits;
-                next_base = claim(a);
+            if (u >= nunits) return false;
+            while (u >= sg.unit_end) sg = get_seg(a, ++seg);
+            up = unit_pos<C>(sg, u);
+            u += step;
+            t = 0;
+            first = true;
+        }
+    }
+};
+
+#if defined(__CUDACC__)
+// Device tile source: every member is executed by ALL lanes of the warp (warp-convergent); results are warp-uniform.
+template <typename C>
+struct TileSrc {
+    uint32_t nunits, pending;          // pending (lane 0): the unit claimed while the previous one was being set up
+    uint32_t seg, seg_unit_end;        // current segment
+    UnitPos up;
+    uint32_t t_next, batch;            // next tile of the unit to hand out; tile index held by lane 0
+    uint32_t phase0, period;
+    float r;
+    bool first;
+    uint32_t dk0, dns, dskip, dinfo;   // lane-held: tile (batch + lane) of the unit
+
+    __device__ __forceinline__ void init(const MixArgs& a, uint32_t lane)
+    {
+        nunits = a.nunits;
+        pending = lane == 0 ? atomicAdd(a.unit_counter, 1u) : 0u;
+        seg = 0;
+        seg_unit_end = get_seg(a, 0).unit_end;
+        up.ntiles = up.c = up.j0 = 0;
+        t_next = batch = 0;
+        phase0 = period = 0;
+        r = 0.0f;
+        first = false;
+        dk0 = dns = dskip = dinfo = 0;
+    }
+
+    __device__ __forceinline__ void expand(const DevSeg& sg, uint32_t lane)
+    {
+        const uint32_t t = batch + lane;
+        dns = 0;
+        if (t < up.ntiles) unit_tile<C>(sg, up, t, dk0, dns, dskip, dinfo);
+    }
+
+    // Next tile of this warp's stream of work; false when the launch has no more work for it.
+    __device__ __forceinline__ bool fetch(const MixArgs& a, uint32_t lane, TileDesc& d)
+    {
+        for (;;) {
+            if (t_next < up.ntiles) {
+                if (t_next >= batch + 32u) {   // units of more than 32 rows: the next 32
+                    batch += 32u;
+                    expand(get_seg(a, seg), lane);
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, dns != 0u) & (0xffffffffu << (t_next - batch));
+                if (m == 0u) {
+                    t_next = batch + 32u;
+                    continue;
+                }
+                const int l = __ffs((int)m) - 1;
+                t_next = batch + (uint32_t)l + 1u;
+                d.k0 = __shfl_sync(0xffffffffu, dk0, l);
+                d.nsamp = __shfl_sync(0xffffffffu, dns, l);
+                d.skip = __shfl_sync(0xffffffffu, dskip, l);
+                d.info = __shfl_sync(0xffffffffu, dinfo, l) | (first && period ? kColFirst : 0u);
+                d.seg = seg;
+                d.phase0 = phase0;
+                d.period = period;
+                d.r = r;
+                first = false;
+                return true;
             }
-            if (u >= sg.unit_end) {
+            const uint32_t u = __shfl_sync(0xffffffffu, pending, 0);
+            if (u >= nunits) return false;
+            if (lane == 0) pending = atomicAdd(a.unit_counter, 1u);   // for the unit after this one: its latency hides behind this unit
+            if (u >= seg_unit_end) {
                 // jump through the coarse unit -> segment index, then walk the last few segments
                 if (a.nsegs > (uint32_t)kInlineSegs) {
                     const uint32_t hint = a.seg_index[u >> kSegIndexShift];
                     if (hint > seg) seg = hint - 1;
                 }
-                do sg = get_seg(a, ++seg);
-                while (u >= sg.unit_end);
+                do seg_unit_end = get_seg(a, ++seg).unit_end;
+                while (u >= seg_unit_end);
             }
-            const uint32_t v = u - sg.unit_begin;
-            u++;
-            if (sg.rows == 0) {
-                const uint32_t ntiles = (sg.k_end - sg.k_begin + T - 1) / T;
-                j = v * kGridUnitTiles;
-                jend = j + kGridUnitTiles < ntiles ? j + kGridUnitTiles : ntiles;
-                continue;
-            }
-            const uint32_t g = (uint32_t)(((uint64_t)v * sg.ncols_magic) >> sg.ncols_shift);
-            c = v - g * sg.ncols;
-            j = g * sg.rows_per_unit;
-            jend = j + sg.rows_per_unit < sg.rows ? j + sg.rows_per_unit : sg.rows;
+            const DevSeg sg = get_seg(a, seg);
+            up = unit_pos<C>(sg, u);
+            phase0 = sg.rows ? up.c * (uint32_t)C::kTileSamples : sg.piece;
+            period = sg.rows ? sg.period : 0u;
+            r = sg.rows ? sg.r : 0.0f;
+            batch = 0;
+            t_next = 0;
             first = true;
+            expand(sg, lane);
         }
     }
 };
+#endif
 
 template <int IN, int OUT, int WARPS, int S, int U>
 __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_constant__ MixArgs a)
@@ -788,23 +907,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
     const unsigned char* gin = static_cast<const unsigned char*>(a.in);
     unsigned char* gout = static_cast<unsigned char*>(a.out);
 
-    // lane 0: iterator + load issue; the descriptor travels to the compute stage through shared memory
-    TileIter<C> it;
-    if (lane == 0) it.init(a, pipe, npipes);   // lane 0 only: init claims a chunk of work units
-    auto issue_next = [&](uint32_t s) {   // lane 0 only
+    // the warp expands its work units into tiles together (TileSrc); lane 0 issues the tile's bulk load and parks the
+    // descriptor in shared memory for the compute stage
+    TileSrc<C> src;
+    src.init(a, lane);
+    auto issue_next = [&](uint32_t s) {   // all lanes (warp-convergent)
         TileDesc d;
-        if (it.next(a, d)) {
-            const uint32_t bytes = (d.nsamp - d.skip) * kInBps;
-            mbar_expect_tx(&full[s], bytes);
-            bulk_g2s(ring_in + s * C::kTileIn + d.skip * kInBps, gin + (size_t)(d.k0 + d.skip) * kInBps, bytes, &full[s]);
-        } else {
-            d.k0 = d.nsamp = d.seg = d.info = d.phase0 = d.period = d.skip = 0;
-            d.r = 0.0f;
+        const bool more = src.fetch(a, lane, d);
+        if (lane == 0) {
+            if (more) {
+                const uint32_t bytes = (d.nsamp - d.skip) * kInBps;
+                mbar_expect_tx(&full[s], bytes);
+                bulk_g2s(ring_in + s * C::kTileIn + d.skip * kInBps, gin + (size_t)(d.k0 + d.skip) * kInBps, bytes, &full[s]);
+            } else {
+                d.k0 = d.nsamp = d.seg = d.info = d.phase0 = d.period = d.skip = 0;
+                d.r = 0.0f;
+            }
+            desc_ring[s] = d;
         }
-        desc_ring[s] = d;
     };
-    if (lane == 0)
-        for (uint32_t s = 0; s < (uint32_t)S; s++) issue_next(s);
+    for (uint32_t s = 0; s < (uint32_t)S; s++) issue_next(s);
 
     // (optionally) one piece's table de-interleaved into shared memory
     uint32_t plane_len = 0;
@@ -843,7 +965,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
         __syncwarp();                              // in[s] and desc[s] are in registers now
         bool refilled = false;
         if (d.info & kColFlag) {
-            if (lane == 0) issue_next(s);
+            issue_next(s);
             refilled = true;
             if (d.info & kColFirst) {
                 eval_window<C>(win, d.r, d.period, d.phase0, lane);
@@ -861,10 +983,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
             }
             const bool fast = k0 + d.nsamp <= p.k_end;
             if (fast) {
-                if (lane == 0) issue_next(s);
+                issue_next(s);
                 refilled = true;
                 if (p.tab == kNoTab)
-                    stream_tile_direct<C, IN, OUT>(raw, out_s, p, k0, lane);
+                    stream_tile_direct<C, IN, OUT>(raw, out_s, p, k0, lane, win);   // the COLUMN window doubles as the plateau scratch
                 else if (pi == a.smem_piece)
                     stream_tile<C, IN, OUT, kTabShared>(raw, out_s, p, k0, tab_s, plane_len, lane);
                 else
@@ -874,7 +996,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
                 __syncwarp();
             }
         }
-        if (!refilled && lane == 0) issue_next(s);
+        if (!refilled) issue_next(s);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -913,9 +1035,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_grid_kernel(const __grid_co
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     unsigned char* rings = smem + C::kBarBytes;
-    float2* tab_s = reinterpret_cast<float2*>(smem + C::kGridSmem);
-
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // launches of the direct-evaluation shape carry a per-warp plateau scratch between the rings and the table
+    float2* scratch = a.plateau_scratch ? reinterpret_cast<float2*>(smem + C::kGridSmem + warp * C::kPlateauBytes) : nullptr;
+    float2* tab_s = reinterpret_cast<float2*>(smem + C::kGridSmem + (a.plateau_scratch ? WARPS * C::kPlateauBytes : 0));
+
     uint64_t* full = bars + warp * S;
     unsigned char* ring_in = rings + warp * C::kRing;
     unsigned char* ring_out = ring_in + S * C::kTileIn;
@@ -984,7 +1108,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_grid_kernel(const __grid_co
             __syncwarp();
             if (lane == 0 && i + S < mine) issue_load(i + S);   // in[s] is in registers now: refill it
             if (p.tab == kNoTab)
-                stream_tile_direct<C, IN, OUT>(raw, out_s, p, k0, lane);
+                stream_tile_direct<C, IN, OUT>(raw, out_s, p, k0, lane, scratch);
             else if (pi == a.smem_piece)
                 stream_tile<C, IN, OUT, kTabShared>(raw, out_s, p, k0, tab_s, plane_len, lane);
             else
@@ -1040,63 +1164,74 @@ struct SmallDone {
     uint32_t token;
 };
 
-template <int IN, int OUT>
+// V groups per thread per step, all V loads issued before the first is used (memory-level parallelism: the tiny
+// zero-copy launches are one CTA and pay a PCIe round trip per dependent load; the mid sizes want bytes in flight).
+template <int IN, int OUT, int V>
 __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_constant__ MixArgs a, const SmallDone done)
 {
     constexpr int G = group_samples(IN, OUT);
+    constexpr uint32_t kStep = kSmallThreads * V;
     const uint32_t ngroups = a.nsamples / G;
-    const uint32_t stride = gridDim.x * kSmallThreads;
     uint32_t pi = 0;
     DevPiece p = get_piece(a, 0);
-    for (uint32_t g = blockIdx.x * kSmallThreads + threadIdx.x; g < ngroups; g += stride) {
-        const uint32_t k0 = g * G;
-        uint32_t w[4] = {0, 0, 0, 0};
-        if constexpr (IN == I16 && G == 4) {
-            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(a.in) + g);
-            w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
-        } else if constexpr (IN == I16) {
-            const uint2 v = __ldcs(reinterpret_cast<const uint2*>(a.in) + g);
-            w[0] = v.x, w[1] = v.y;
-        } else {
-            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(a.in) + g);
-            w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
-        }
-        float2 smp[G], res[G];
-        if constexpr (IN == I16) {
+    for (uint32_t base = blockIdx.x * kStep; base < ngroups; base += gridDim.x * kStep) {
+        uint32_t w[V][4];
 #pragma unroll
-            for (int i = 0; i < G; i++) smp[i] = ingest_i16(w[i]);
-        } else {
-            smp[0] = make_float2(__uint_as_float(w[0]), __uint_as_float(w[1]));
-            smp[1] = make_float2(__uint_as_float(w[2]), __uint_as_float(w[3]));
-        }
-        if (k0 >= p.k_end) {
-            pi = find_piece(a, pi, k0);
-            p = get_piece(a, pi);
-        }
-        if (k0 + G <= p.k_end && p.tab != kNoTab) {
-            // inside one tabled piece: entries j .. j+G-1 of its table (replicated kTabPad >= G-1 entries past the period)
-            const float2* tab = a.tables + p.tab + (piece_samplenum(p, k0 - p.k_begin) - 1u);
-#pragma unroll
-            for (int i = 0; i < G; i++) res[i] = cmul_unfused(smp[i], __ldg(tab + i));
-        } else {
-            uint32_t qi = pi;
-            DevPiece q = p;
-#pragma unroll
-            for (int i = 0; i < G; i++) {
-                const uint32_t k = k0 + (uint32_t)i;
-                if (k >= q.k_end) {
-                    qi = find_piece(a, qi, k);
-                    q = get_piece(a, qi);
+        for (int v = 0; v < V; v++) {
+            const uint32_t g = base + v * kSmallThreads + threadIdx.x;
+            w[v][0] = w[v][1] = w[v][2] = w[v][3] = 0;
+            if (g < ngroups) {
+                if constexpr (IN == I16 && G == 2) {
+                    const uint2 x = __ldcs(reinterpret_cast<const uint2*>(a.in) + g);
+                    w[v][0] = x.x, w[v][1] = x.y;
+                } else {
+                    const uint4 x = __ldcs(reinterpret_cast<const uint4*>(a.in) + g);
+                    w[v][0] = x.x, w[v][1] = x.y, w[v][2] = x.z, w[v][3] = x.w;
                 }
-                res[i] = cmul_unfused(smp[i], phasor(q.r, piece_samplenum(q, k - q.k_begin)));
             }
         }
-        if constexpr (OUT == I16 && G == 4) {
-            __stcs(reinterpret_cast<uint4*>(a.out) + g, make_uint4(egress_i16(res[0]), egress_i16(res[1]), egress_i16(res[2]), egress_i16(res[3])));
-        } else if constexpr (OUT == I16) {
-            __stcs(reinterpret_cast<uint2*>(a.out) + g, make_uint2(egress_i16(res[0]), egress_i16(res[1])));
-        } else {
-            __stcs(reinterpret_cast<float4*>(a.out) + g, make_float4(res[0].x, res[0].y, res[1].x, res[1].y));
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            const uint32_t g = base + v * kSmallThreads + threadIdx.x;
+            if (g >= ngroups) break;
+            const uint32_t k0 = g * G;
+            float2 smp[G], res[G];
+            if constexpr (IN == I16) {
+#pragma unroll
+                for (int i = 0; i < G; i++) smp[i] = ingest_i16(w[v][i]);
+            } else {
+                smp[0] = make_float2(__uint_as_float(w[v][0]), __uint_as_float(w[v][1]));
+                smp[1] = make_float2(__uint_as_float(w[v][2]), __uint_as_float(w[v][3]));
+            }
+            if (k0 >= p.k_end) {
+                pi = find_piece(a, pi, k0);
+                p = get_piece(a, pi);
+            }
+            if (k0 + G <= p.k_end && p.tab != kNoTab) {
+                // inside one tabled piece: entries j .. j+G-1 of its table (replicated kTabPad >= G-1 entries past the period)
+                const float2* tab = a.tables + p.tab + (piece_samplenum(p, k0 - p.k_begin) - 1u);
+#pragma unroll
+                for (int i = 0; i < G; i++) res[i] = cmul_unfused(smp[i], __ldg(tab + i));
+            } else {
+                uint32_t qi = pi;
+                DevPiece q = p;
+#pragma unroll
+                for (int i = 0; i < G; i++) {
+                    const uint32_t k = k0 + (uint32_t)i;
+                    if (k >= q.k_end) {
+                        qi = find_piece(a, qi, k);
+                        q = get_piece(a, qi);
+                    }
+                    res[i] = cmul_unfused(smp[i], phasor(q.r, piece_samplenum(q, k - q.k_begin)));
+                }
+            }
+            if constexpr (OUT == I16 && G == 4) {
+                __stcs(reinterpret_cast<uint4*>(a.out) + g, make_uint4(egress_i16(res[0]), egress_i16(res[1]), egress_i16(res[2]), egress_i16(res[3])));
+            } else if constexpr (OUT == I16) {
+                __stcs(reinterpret_cast<uint2*>(a.out) + g, make_uint2(egress_i16(res[0]), egress_i16(res[1])));
+            } else {
+                __stcs(reinterpret_cast<float4*>(a.out) + g, make_float4(res[0].x, res[0].y, res[1].x, res[1].y));
+            }
         }
     }
     // ragged end (fewer samples than a group): one thread each
@@ -1110,7 +1245,9 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
         __threadfence_system();   // this thread's stores (possibly into host memory) are visible before the flag can be
         __syncthreads();
         if (threadIdx.x == 0) {
-            if (atomicAdd(done.counter, 1u) == gridDim.x - 1u) {
+            if (gridDim.x == 1) {
+                *done.flag = done.token;
+            } else if (atomicAdd(done.counter, 1u) == gridDim.x - 1u) {
                 *done.counter = 0u;
                 __threadfence_system();
                 *done.flag = done.token;

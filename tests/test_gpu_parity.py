@@ -231,6 +231,12 @@ DIRECT_CASES = [
     (1000.25, 48_000, 0, 150_000),                   # medium -> large within a few hundred samples
     (123_456.7, 48_000, 5, 60_000),                  # |r| > 1: large from the second sample on
     (-0.37, 1_000_000, 1_000_000, 400_000),          # small/medium boundary region
+    # plateaus of f32(samplenum) above 2^24 at launch sizes that take the bulk-async direct shape: one phasor per distinct
+    # f32(n) of a tile, parked in shared memory (mixer_kernels.cuh, stream_tile_direct)
+    (1.0, 2_000_000_000, 2**24 - 1000, 5_000_000),   # crossing into the plateau region (pairs)
+    (1.0, 2_000_000_000, 2**26 + 12_345, 5_000_000), # plateaus of 8, binade crossing at 2^26 + 2^26
+    (3.0, 2_000_000_000, 2**31 - 2_000_000, 4_500_000),   # 128 -> 256 wide plateaus across 2^31
+    (1.0e-3, 4_000_000_000, 2**32 - 3_000_000, 5_000_000),   # up to f32(n) = 2^32, the u32 wrap, the reset at 0, then tiny angles
 ]
 
 
@@ -340,6 +346,24 @@ def test_host_path_multi_chunk_with_long_periods(oracle, mixer):
     want, sn_ref = oracle.mix_blocks(buf[:nbytes], I16, F32, shifts, 1_024_000)
     assert sn == sn_ref
     check(oracle, got, want, F32)
+
+
+def test_plateau_piece_inside_a_segmented_launch(oracle, mixer):
+    """A launch with COLUMN segments whose first piece is a never-resetting run above 2^24: the segmented kernel takes
+    the plateau path for its GRID tiles, with the COLUMN window as scratch."""
+    rng = np.random.default_rng(77)
+    fs = 1_024_000
+    bs = BUFFER_SIZE // 4
+    shifts = np.concatenate([np.repeat(np.float32(1.0e-4), 1000), np.repeat(np.float32(-9876.54), 2200)])   # ~2 M + ~4.5 M samples
+    n = shifts.size * bs - 333
+    for intype, outtype in [(I16, I16), (F32, F32)]:
+        bsz = BUFFER_SIZE // BPS[intype]
+        m = min(n, shifts.size * bsz - 333)
+        buf = make_input(rng, m, intype)
+        got, sn = mixer.mix_blocks(buf, intype, outtype, shifts, fs, samplenum=2**25 + 7)
+        want, sn_ref = oracle.mix_blocks_threads(buf, intype, outtype, shifts, fs, samplenum=2**25 + 7)
+        assert sn == sn_ref
+        check(oracle, got, want, outtype)
 
 
 @pytest.mark.parametrize("shift,fs", [(float("inf"), 48000), (float("-inf"), 48000), (float("nan"), 48000), (1000.0, 0), (0.0, 0),

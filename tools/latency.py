@@ -33,6 +33,20 @@ def device_side(out):
     mixers = {"small": doppler_b200.Mixer(0), "bulk": doppler_b200.Mixer(0)}
     mixers["small"].tune(small_max_samples=1 << 30)
     mixers["bulk"].tune(small_max_samples=0)
+    # the floor of this protocol: the smallest possible kernel (a 4-byte fill) between the same two events after the same flush
+    one = torch.zeros(1, dtype=torch.int32, device=dev)
+    ts = []
+    with torch.cuda.stream(stream):
+        for i in range(23):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            one.fill_(i)
+            e1.record(stream)
+            stream.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1) * 1e3)
+    out({"what": "protocol floor", "kernel": "torch fill_ of 4 bytes", "us_median": statistics.median(ts), "us_best": min(ts)})
     cases = [("P=256 table", -15000.0, 256000), ("irregular direct", 7321.0, 1_024_000)]
     for label, shift, fs in cases:
         for n in [2048, 65_536, 256_000, 1_024_000, 2_000_000, 4_000_000, 10_000_000, 20_000_000, 40_000_000, 100_000_000]:

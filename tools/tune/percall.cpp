@@ -1,9 +1,11 @@
 // tools/tune/percall.cpp -- latency of the host-buffer C-ABI calls at the reference's own granularity
-// (one 8192-byte block per call, src/main.rs:49,70) and at the batched sizes INTEGRATION.md recommends.
+// (one 8192-byte block per call, src/main.rs:49,70) and at the batched sizes INTEGRATION.md recommends,
+// with the zero-copy tiny path on (default) and off, pageable and pinned caller buffers.
 // Build: make -C tools/tune percall      Run (GPU box): tools/tune/percall
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "../../include/doppler_b200.h"
@@ -16,18 +18,41 @@ int main()
         return 2;
     }
     auto now = [] { return std::chrono::steady_clock::now(); };
-    const size_t sizes[] = {1024, 16384, 262144, 4194304, 33554432};   // complex samples per call
-    for (size_t n : sizes) {
-        std::vector<float> in(2 * n, 0.25f), out(2 * n);
-        uint32_t sn = 0;
-        const int iters = n <= 16384 ? 4000 : n <= 262144 ? 1000 : n <= 4194304 ? 100 : 20;
-        for (int i = 0; i < 20; i++) doppler_b200_shift_frequency(ctx, in.data(), n, &sn, 815000.0f, 2400000, out.data());
-        auto t0 = now();
-        for (int i = 0; i < iters; i++)
-            if (doppler_b200_shift_frequency(ctx, in.data(), n, &sn, 815000.0f, 2400000, out.data()) != 0) return 3;
-        const double us = std::chrono::duration<double, std::micro>(now() - t0).count() / iters;
-        printf("{\"call\": \"doppler_b200_shift_frequency (pageable host buffers)\", \"samples_per_call\": %zu, \"us_per_call\": %.1f, "
-               "\"msps\": %.1f}\n", n, us, n / us);
+    const size_t sizes[] = {1024, 2048, 16384, 262144, 4194304, 33554432};   // complex samples per call
+    for (int tiny = 1; tiny >= 0; tiny--) {
+        doppler_b200_tune(ctx, DOPPLER_B200_TUNE_TINY_HOST_BYTES, tiny ? (128u << 10) : 0);
+        for (int pinned = 0; pinned < 2; pinned++)
+            for (size_t n : sizes) {
+                if (pinned && n > 262144) continue;
+                const size_t bytes = n * 4;   // i16 IQ in and out
+                void *in, *out;
+                if (pinned) {
+                    in = doppler_b200_host_alloc(bytes);
+                    out = doppler_b200_host_alloc(bytes);
+                } else {
+                    in = malloc(bytes);
+                    out = malloc(bytes);
+                }
+                memset(in, 1, bytes);
+                uint32_t sn = 0;
+                size_t got = 0;
+                const int iters = n <= 16384 ? 5000 : n <= 262144 ? 1000 : n <= 4194304 ? 100 : 20;
+                for (int i = 0; i < 50; i++) doppler_b200_mix(ctx, in, bytes, DOPPLER_B200_I16, DOPPLER_B200_I16, 5000.0f, 1024000, &sn, out, bytes, &got);
+                auto t0 = now();
+                for (int i = 0; i < iters; i++)
+                    if (doppler_b200_mix(ctx, in, bytes, DOPPLER_B200_I16, DOPPLER_B200_I16, 5000.0f, 1024000, &sn, out, bytes, &got) != 0) return 3;
+                const double us = std::chrono::duration<double, std::micro>(now() - t0).count() / iters;
+                printf("{\"call\": \"doppler_b200_mix i16->i16\", \"zero_copy_tiny_path\": %s, \"caller_buffers\": \"%s\", \"samples_per_call\": %zu, "
+                       "\"us_per_call\": %.2f, \"msps\": %.1f}\n", tiny ? "true" : "false", pinned ? "pinned" : "pageable", n, us, n / us);
+                fflush(stdout);
+                if (pinned) {
+                    doppler_b200_host_free(in);
+                    doppler_b200_host_free(out);
+                } else {
+                    free(in);
+                    free(out);
+                }
+            }
     }
     doppler_b200_destroy(ctx);
     return 0;
