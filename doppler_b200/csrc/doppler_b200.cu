@@ -7,6 +7,7 @@
 // 3-slot pinned/stream pipeline (H2D, kernel and D2H of neighbouring chunks overlap).  No CPU
 // implementation of the mixer exists in this library.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -61,7 +62,8 @@ namespace {
 
 constexpr uint64_t kLaunchMaxSamples = 1ull << 30;   // k fits 32 bits with room for base + offset
 constexpr uint32_t kColumnMaxRows = 64;              // COLUMN segments: rows sharing one phasor evaluation, at most
-constexpr uint32_t kUnitsPerPipe = 16;               // ... halved until the launch has this many work units per pipeline
+constexpr uint32_t kUnitsPerPipe = 4;                // ... halved once if the launch has fewer work units per pipeline than this
+constexpr double kWindowCostTiles = 1.3;             // issue cost of one COLUMN window evaluation, in tiles (ncu: ~650 vs ~510 instructions)
 constexpr uint32_t kColumnMinRows = 2;               // fewer whole periods than this: evaluate per sample instead
 constexpr uint32_t kColumnMinLaunch = 4u << 20;      // launches below this many samples are latency-bound: a serial window
                                                      // evaluation per work unit costs more than it saves (measured 23 vs 13 us at 1 M)
@@ -292,7 +294,16 @@ uint32_t build_segments(const std::vector<DevPiece>& dev, uint32_t nsamp, uint32
 {
     const uint32_t gmask = ~(gran - 1u), tail_begin = nsamp & gmask;
     std::vector<DevSeg>& segs = *out;
-    for (uint32_t rcap = kColumnMaxRows;; rcap /= 2) {
+    // Rows per COLUMN unit.  More rows amortise the unit's window evaluation (about kWindowCostTiles tiles' worth of issue
+    // slots) over more tiles; fewer, shorter units leave less work unbalanced at the end of the launch (units are claimed
+    // dynamically, so the idle tail is about half a unit per pipeline).  Per-tile cost ~ kWindowCostTiles / R + R / (2 * tiles
+    // per pipeline) is smallest at R = sqrt(2 * kWindowCostTiles * tiles per pipeline).  (Round 1 halved R until the launch had
+    // 16 units per pipeline: R = 8 at 256 M samples, where the window evaluations were 15 % of all issued instructions --
+    // profiles/r02_ncu_column_i16_i16_before.txt.)
+    const double tiles_per_pipe = (double)nsamp / T / (npipes ? npipes : 1);
+    uint32_t rcap0 = (uint32_t)sqrt(2.0 * kWindowCostTiles * tiles_per_pipe);
+    rcap0 = std::max(kColumnMinRows, std::min(kColumnMaxRows, rcap0));
+    for (uint32_t rcap = rcap0;; rcap /= 2) {
         segs.clear();
         uint32_t cursor = 0, cursor_piece = 0, units = 0;
         auto push_grid = [&](uint32_t b, uint32_t e, uint32_t piece) {
@@ -344,7 +355,7 @@ uint32_t build_segments(const std::vector<DevPiece>& dev, uint32_t nsamp, uint32
         push_grid(cursor, tail_begin, cursor_piece);
         // fewer rows per unit (more, shorter units) until the pipelines can balance: units are claimed
         // dynamically, so the end-of-launch idle time is about one unit in kUnitsPerPipe
-        if (units >= kUnitsPerPipe * npipes || rcap <= kColumnMinRows) break;
+        if (units >= kUnitsPerPipe * npipes || rcap / 2 < kColumnMinRows || rcap * 2 <= rcap0) break;   // at most one halving: keep some slack for balance
     }
     return tail_begin;
 }

@@ -548,15 +548,21 @@ __device__ __forceinline__ void stream_tile_direct(const uint32_t (&raw)[C::U][4
     db_window_t dt;
     const int range = mono ? classify_tile(r, n0, n0 + (kTile - 1u), dt) : (int)kRangeGeneric;
     const uint32_t nl = n0 + lane * C::G;   // this lane's first samplenum in row 0
-    if (mono && scratch != nullptr && n0 >= (1u << 24)) {
+    // Only for i16 output: those pairs move 8-12 bytes per sample and direct evaluation makes them issue-bound, so fewer
+    // evaluations win (0.755 -> 0.89 of the HBM peak for i16->i16).  With f32 output the per-sample evaluation already fits
+    // under the HBM time, and the evaluate -> park -> barrier -> look up chain only adds exposed latency (measured 0.97 -> 0.90).
+    if (OUT == I16 && mono && scratch != nullptr && n0 >= (1u << 24)) {
         const uint32_t b0 = __float_as_uint(__uint2float_rn(n0));
         const uint32_t nvals = __float_as_uint(__uint2float_rn(n0 + (kTile - 1u))) - b0 + 1u;   // <= kTile / 2 + 1
         auto theta_e = [&](uint32_t e) { return __fmul_rn(__uint_as_float(0xC0C90FDBu), __fmul_rn(r, __uint_as_float(b0 + e))); };
         if (range == kRangeLarge) {
+#pragma unroll 2
             for (uint32_t e = lane; e < nvals; e += 32) scratch[e] = phasor_fast<kRangeLarge>(theta_e(e), dt);
         } else if (range == kRangeMedium) {
+#pragma unroll 2
             for (uint32_t e = lane; e < nvals; e += 32) scratch[e] = phasor_fast<kRangeMedium>(theta_e(e), dt);
         } else if (range == kRangeSmall) {
+#pragma unroll 2
             for (uint32_t e = lane; e < nvals; e += 32) scratch[e] = phasor_fast<kRangeSmall>(theta_e(e), dt);
         } else if (range == kRangeTiny) {
             for (uint32_t e = lane; e < nvals; e += 32) scratch[e] = phasor_fast<kRangeTiny>(theta_e(e), dt);

@@ -138,7 +138,7 @@ def main():
     cases.append(("cfg5 irregular 7321 Hz @ 1.024 Msps, 1 s", I16, I16, 7321.0, 1_024_000, 1_024_000))
     cases.append(("cfg2 f32->i16 10 Msps shift 100000, 64 s", F32, I16, 100000.0, 10_000_000, 640_000_000 if not args.quick else 64_000_000))
     if args.only:
-        cases = [c for c in cases if any(f in c[0] for f in args.only.split(","))]
+        cases = [c for c in cases if any(f.replace("_", " ") in c[0] for f in args.only.split(","))]   # "_" stands for a blank (shell-friendly)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     recs = []
     with open(args.out, "w") as f:
@@ -161,7 +161,7 @@ def main():
             track.append(("cfg4 track f32->f32 @ 200 Msps, slice 3 of 8 (1.5 G samples)", F32, F32, 200_000_000,
                           sh[b // slicing.block_samples(F32):], e - b, slicing.seed_blocks(sh, F32, 200_000_000, b)))
         for c in track:
-            if args.only and not any(f in c[0] for f in args.only.split(",")):
+            if args.only and not any(f.replace("_", " ") in c[0] for f in args.only.split(",")):
                 continue
             rec = run_track_case(mixer, stream, *c, max(3, args.iters // 4))
             recs.append(rec)
