@@ -78,6 +78,8 @@ SIGNATURES = {
     "doppler_b200_tracker_create_from_lines": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_double,
                                                                ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_void_p)]),
     "doppler_b200_tracker_destroy": (None, [ctypes.c_void_p]),
+    "doppler_b200_tracker_is_deep_space": (ctypes.c_int, [ctypes.c_void_p]),
+    "doppler_b200_orbit_constants": (ctypes.c_int, [ctypes.c_int]),
     "doppler_b200_tracker_last_error": (ctypes.c_char_p, []),
     "doppler_b200_tracker_observe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double] + [ctypes.POINTER(ctypes.c_double)] * 4),
     "doppler_b200_tracker_teme": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),

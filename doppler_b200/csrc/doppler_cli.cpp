@@ -5,7 +5,9 @@
 // short read, one shift per block in track mode, samplenum carried), but pumps the stream in large
 // chunks: a reader thread fills pinned buffers, the GPU mixes a whole chunk per call
 // (doppler_b200_mix / doppler_b200_mix_blocks reproduce the per-block chain internally), a writer
-// thread drains.  stdout is byte-identical to the reference's for the same stdin.  Chunks are
+// thread drains.  stdout is byte-identical to the reference's for the same stdin in const mode and for a given
+// per-second Doppler table (--doppler-table); with --tlefile the Doppler comes from this build's own SGP4 / SDP4
+// (orbit.cpp) instead of libgpredict, so the output is functionally equivalent, not byte-identical.  Chunks are
 // ADAPTIVE: the reader dispatches what has arrived (whole blocks) as soon as stdin goes idle for
 // kIdleMicros, so a live 1 Msps pipe sees millisecond latency (the reference: one 8 KiB block) while
 // a fast producer fills 32 MiB chunks.
@@ -465,6 +467,8 @@ int main(int argc, char** argv)
             }
             use_tracker = true;
             INFO("\tfrequency       : %u Hz", args.frequency);
+            INFO("\tpropagator      : built-in %s, %s constants (stands in for libgpredict: equivalent Doppler, not bit-identical output)",
+                 tracker.deep_space() ? "SDP4" : "SGP4", tracker.consts().name);
         }
         if (args.have_time) {
             time_t t = (time_t)args.start_unix;

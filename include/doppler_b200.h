@@ -231,16 +231,28 @@ size_t doppler_b200_replay_schedule(const double* doppler_hz_by_second, size_t n
 /* ---- orbit propagation for track mode (host only; replaces crate gpredict / libgpredict) --- */
 
 /* Tle::from_file + Predict::new (src/main.rs:141-149): TLE `tlename` from `tlefile`, observer at
- * lat/lon (degrees) and altitude (metres).  SGP4 near-earth model (Spacetrack Report No. 3);
- * deep-space element sets and bad checksums are rejected (EINVAL, see
- * doppler_b200_tracker_last_error).  Parity with libgpredict is UNPINNED (not available offline);
- * the propagator is verified against the report's own test case instead. */
+ * lat/lon (degrees) and altitude (metres).  SGP4 for near-earth element sets, SDP4 (lunar-solar
+ * and resonance terms) for periods >= 225 min, both after Spacetrack Report No. 3 and verified
+ * against its test cases; bad checksums are rejected (EINVAL, doppler_b200_tracker_last_error).
+ * Parity with libgpredict is UNPINNED (not available offline): track mode from a TLE is functionally
+ * equivalent to the reference, not byte-identical -- byte parity is claimed for const mode and for a
+ * given Doppler table (doppler_b200_replay_schedule) only. */
 typedef struct doppler_b200_tracker doppler_b200_tracker;
 int doppler_b200_tracker_create(const char* tlefile, const char* tlename, double lat_deg, double lon_deg, double alt_m,
                                 doppler_b200_tracker** out);
 int doppler_b200_tracker_create_from_lines(const char* name, const char* line1, const char* line2, double lat_deg, double lon_deg,
                                            double alt_m, doppler_b200_tracker** out);
 void doppler_b200_tracker_destroy(doppler_b200_tracker* tr);
+/* 1 when the element set takes the deep-space model (SDP4), 0 for SGP4. */
+int doppler_b200_tracker_is_deep_space(const doppler_b200_tracker* tr);
+
+/* Physical constants of trackers created afterwards; returns the previous choice (any other argument only
+ * queries).  GPREDICT (default; env DOPPLER_B200_ORBIT_CONSTANTS=gpredict|wgs72): the values libgpredict's
+ * sgp4sdp4.h carries -- WGS-84 radius / flattening next to the WGS-72 gravity field, rounded qoms2t, s and
+ * earth rotation rate -- recalled, not verifiable offline.  WGS72: Spacetrack Report No. 3's own set. */
+#define DOPPLER_B200_ORBIT_GPREDICT 0
+#define DOPPLER_B200_ORBIT_WGS72 1
+int doppler_b200_orbit_constants(int which);
 const char* doppler_b200_tracker_last_error(void);
 
 /* Predict::update(Some(t)) (src/main.rs:162) and the fields the reference reads afterwards

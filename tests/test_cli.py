@@ -170,6 +170,45 @@ def test_track_replay_with_tle_matches_library_schedule(oracle, tmp_path):
     assert b"range rate" in r.stderr   # main.rs:167-175 telemetry every 5 s of stream time
 
 
+def _synthetic_estcube_tle():
+    """A SYNTHETIC, checksum-valid element set shaped like ESTCube-1's orbit (660 km sun-synchronous, 98.1 deg) with an
+    epoch next to the README's recording time.  NOT a real ESTCube-1 TLE -- none is available offline."""
+    def ck(line):
+        return line + str(sum((int(c) if c.isdigit() else (1 if c == "-" else 0)) for c in line[:68]) % 10)
+    l1 = ck("1 39161U 13021C   15021.50000000  .00001200  00000-0  20000-3 0  999")
+    l2 = ck("2 39161  98.1300  99.5000 0010000 200.0000 160.0000 14.69000000 9000")
+    assert len(l1) == 69 and len(l2) == 69
+    return "ESTCUBE 1\n" + l1 + "\n" + l2 + "\n"
+
+
+@pytest.mark.gpu
+def test_readme_recording_command_with_a_synthetic_estcube_tle(oracle, tmp_path):
+    """README.md:59 verbatim (`--tlename 'ESTCUBE 1' --location lat=58.26541,lon=26.46667,alt=76 --frequency 437505000
+    --offset -2500 --time 2015-01-22T09:07:16`, 256 ksps i16) on a synthetic element set: the CLI's stdout must equal the
+    oracle's replay driver fed with the library's per-second Doppler table, and the Doppler must be that of a LEO pass."""
+    import ctypes
+    from doppler_b200 import _lib
+    f = tmp_path / "cubesat.txt"
+    f.write_text("SOME OTHER SAT\n" + L1 + "\n" + L2 + "\n" + _synthetic_estcube_tle())
+    fs, secs = 256000, 12
+    x = tone_i16(secs * fs + 1234, fs, 22)
+    lib = _lib.load()
+    tr = ctypes.c_void_p()
+    assert lib.doppler_b200_tracker_create(str(f).encode(), b"ESTCUBE 1", 58.26541, 26.46667, 76.0, ctypes.byref(tr)) == 0
+    start = (np.datetime64("2015-01-22T09:07:16") - np.datetime64("1970-01-01T00:00:00")) / np.timedelta64(1, "s")
+    table = np.zeros(secs + 2)
+    lib.doppler_b200_tracker_doppler_table(tr, float(start), 437_505_000, table.size, table.ctypes.data)
+    lib.doppler_b200_tracker_destroy(tr)
+    assert np.abs(table).max() < 11_000.0 and np.ptp(table) > 0.05     # |v_r| < 7.5 km/s at 437.5 MHz; it moves
+    want, _, shifts, panicked = oracle.track_replay_stream(x, I16, I16, table, -2500, fs)
+    assert not panicked
+    r = run(["track", "-s", "256000", "-i", "i16", "--tlefile", str(f), "--tlename", "ESTCUBE 1", "--location",
+             "lat=58.26541,lon=26.46667,alt=76", "--frequency", "437505000", "--offset", "-2500", "--time", "2015-01-22T09:07:16"], x.tobytes())
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == want.tobytes()
+    assert b"propagator" in r.stderr and b"SGP4" in r.stderr and b"doppler@437.505 MHz" in r.stderr
+
+
 @pytest.mark.gpu
 def test_live_pipe_latency_and_trickled_input(oracle):
     """A live producer (rtl_fm at ~1 Msps) delivers a few blocks at a time: the pump must hand back what has

@@ -21,6 +21,22 @@ STR3 = {
 }
 
 
+# Spacetrack Report No. 3, section 13, SDP4 test case (deep space: 10.5 h period, e = 0.73; lunar-solar terms, no resonance)
+D1 = "1 11801U          80230.29629788  .01431103  00000-0  14311-1 0    13"
+D2 = "2 11801  46.7916 230.4354 7318036  47.4722  10.4117  2.28537848    13"
+STR3_DEEP = {
+    0.0: (7473.37066650, 428.95261765, 5828.74786377, 5.10715413, 6.44468284, -0.18613096),
+    360.0: (-3305.22537232, 32410.86328125, -24697.17675781, -1.30113538, -1.15131518, -0.28333528),
+    720.0: (14271.28759766, 24110.46411133, -4725.76837158, -0.32050445, 2.67984074, -2.08405289),
+    1080.0: (-9990.05883789, 22717.35522461, -23616.89062501, -1.01667246, -2.29026759, 0.72892364),
+    1440.0: (9787.86975097, 33753.34667969, -15030.81176758, -1.09425966, 0.92358845, -1.52230928),
+}
+
+
+def checksum(line68):
+    return str(sum((int(c) if c.isdigit() else (1 if c == "-" else 0)) for c in line68[:68]) % 10)
+
+
 def make(l1=L1, l2=L2, lat=58.26541, lon=26.46667, alt=76.0):
     lib = _lib.load()
     tr = ctypes.c_void_p()
@@ -39,14 +55,80 @@ def test_sgp4_reproduces_spacetrack_report_3():
     lib.doppler_b200_tracker_destroy(tr)
 
 
-def test_bad_checksum_and_deep_space_are_rejected():
+def test_bad_checksum_is_rejected():
     lib, tr, rc = make(l1=L1[:-1] + "3")
     assert rc != 0 and b"checksum" in lib.doppler_b200_tracker_last_error()
-    # a geostationary-like mean motion (1.0027 rev/day) is a deep-space object: SDP4 not implemented
-    l2 = "2 88888  72.8435 115.9689 0086731  52.6988 110.5714  1.00270000  105"
-    s = sum((int(c) if c.isdigit() else (1 if c == "-" else 0)) for c in l2[:68]) % 10
-    lib, tr, rc = make(l2=l2 + str(s))
-    assert rc != 0 and b"deep-space" in lib.doppler_b200_tracker_last_error()
+
+
+@pytest.mark.parametrize("which", [0, 1], ids=["gpredict-constants", "wgs72-constants"])
+def test_sdp4_reproduces_spacetrack_report_3(which):
+    """The deep-space model against the report's own case, with either constant set (they differ by 2 m in the earth radius:
+    far below the single-precision print of the report)."""
+    lib = _lib.load()
+    prev = lib.doppler_b200_orbit_constants(which)
+    try:
+        lib, tr, rc = make(D1, D2)
+        assert rc == 0 and lib.doppler_b200_tracker_is_deep_space(tr) == 1
+        for t, exp in STR3_DEEP.items():
+            p, v = np.zeros(3), np.zeros(3)
+            assert lib.doppler_b200_tracker_teme(tr, t, p.ctypes.data, v.ctypes.data) == 0
+            assert np.abs(p - np.array(exp[:3])).max() < 3e-2   # km at radii up to 41 000 km; the report is single precision
+            assert np.abs(v - np.array(exp[3:])).max() < 2e-5   # km/s
+        lib.doppler_b200_tracker_destroy(tr)
+        lib, tr, rc = make()
+        assert lib.doppler_b200_tracker_is_deep_space(tr) == 0
+        for t, exp in STR3.items():                              # SGP4 under the same constant set
+            p, v = np.zeros(3), np.zeros(3)
+            lib.doppler_b200_tracker_teme(tr, t, p.ctypes.data, v.ctypes.data)
+            assert np.abs(p - np.array(exp[:3])).max() < 2e-2 and np.abs(v - np.array(exp[3:])).max() < 2e-5
+        lib.doppler_b200_tracker_destroy(tr)
+    finally:
+        lib.doppler_b200_orbit_constants(prev)
+
+
+def _elements(n_rev_day, ecc, incl, argp=90.0, raan=10.0, ma=0.0):
+    l1 = "1 99999U          15022.50000000  .00000000  00000-0  00000-0 0    1"
+    l1 = l1[:68] + checksum(l1)
+    l2 = "2 99999 %8.4f %8.4f %07d %8.4f %8.4f %11.8f    1" % (incl, raan, round(ecc * 1e7), argp, ma, n_rev_day)
+    assert len(l2) == 68, len(l2)
+    return l1, l2 + checksum(l2)
+
+
+def test_resonant_orbits_stay_physical():
+    """The 24 h and 12 h geopotential-resonance branches have no published vector: check what physics demands of them.
+    Geostationary: radius 42 164 km and a sub-satellite longitude that stays put; Molniya (12 h, e = 0.7): radius between
+    perigee and apogee, period twice per sidereal day; both: speed from vis-viva, continuity across the 720 min integrator steps."""
+    lib = _lib.load()
+    mu = 398600.8
+    for n, ecc, incl, a_km in ((1.00273790, 0.0002, 0.05, 42164.0), (2.00561, 0.70, 63.4, 26555.0)):
+        lib_, tr, rc = make(*_elements(n, ecc, incl))
+        assert rc == 0 and lib.doppler_b200_tracker_is_deep_space(tr) == 1, lib.doppler_b200_tracker_last_error()
+        for t in np.arange(0.0, 4320.0, 90.0):
+            p, v = np.zeros(3), np.zeros(3)
+            lib.doppler_b200_tracker_teme(tr, float(t), p.ctypes.data, v.ctypes.data)
+            r, sp = np.linalg.norm(p), np.linalg.norm(v)
+            assert a_km * (1 - ecc) * 0.995 < r < a_km * (1 + ecc) * 1.005, (n, t, r)
+            assert abs(sp - np.sqrt(mu * (2.0 / r - 1.0 / a_km))) < 0.02 * sp, (n, t, sp)      # vis-viva within 2 %
+        for tb in (720.0, 1440.0, 2160.0, -720.0):                                           # no jump where the integrator steps
+            pa, va, pb, vb = np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(3)
+            lib.doppler_b200_tracker_teme(tr, tb - 1.0 / 60.0, pa.ctypes.data, va.ctypes.data)
+            lib.doppler_b200_tracker_teme(tr, tb + 1.0 / 60.0, pb.ctypes.data, vb.ctypes.data)
+            assert np.linalg.norm(pb - pa - (va + vb)) < 0.05, (n, tb)                       # 2 s of motion at the mean velocity, km
+        # one step forward and back gives the same state (the integrator restarts from the epoch: no call-order dependence)
+        p1, v1, p2, v2 = np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(3)
+        lib.doppler_b200_tracker_teme(tr, 2000.0, p1.ctypes.data, v1.ctypes.data)
+        lib.doppler_b200_tracker_teme(tr, -500.0, p2.ctypes.data, v2.ctypes.data)
+        lib.doppler_b200_tracker_teme(tr, 2000.0, p2.ctypes.data, v2.ctypes.data)
+        assert np.array_equal(p1, p2) and np.array_equal(v1, v2)
+        lib.doppler_b200_tracker_destroy(tr)
+    # the geostationary one again: seen from the ground it hardly moves (range rate of a few m/s at most)
+    lib_, tr, rc = make(*_elements(1.00273790, 0.0002, 0.05), lat=0.0, lon=20.0, alt=0.0)
+    epoch = (np.datetime64("2015-01-22T12:00:00") - np.datetime64("1970-01-01T00:00:00")) / np.timedelta64(1, "s")
+    az, el, rng, rr = (ctypes.c_double() for _ in range(4))
+    for dt in (0.0, 3600.0, 40000.0, 86400.0):
+        assert lib.doppler_b200_tracker_observe(tr, float(epoch + dt), ctypes.byref(az), ctypes.byref(el), ctypes.byref(rng), ctypes.byref(rr)) == 0
+        assert 35700.0 < rng.value < 48600.0 and abs(rr.value) < 0.01   # anywhere between overhead and beyond the limb; standing still
+    lib.doppler_b200_tracker_destroy(tr)
 
 
 def test_range_rate_is_the_derivative_of_range_and_doppler_table_follows_main_rs():
