@@ -15,6 +15,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -112,6 +115,7 @@ struct Slot {
 
 struct doppler_b200_ctx {
     int device = 0;
+    void* copy_pool = nullptr;   // CopyPool (host staging threads), created on first use
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     dplan::Planner planner;
@@ -699,33 +703,98 @@ bool is_pinned(const void* p)
     return at.type == cudaMemoryTypeHost;
 }
 
-// Staging copies between the caller's pageable buffers and the pinned slots: a single thread moves ~10 GB/s,
-// a fifth of what PCIe takes, so large copies are split over a few threads (measured 0.9 -> see
-// profiles/r01_percall_latency.jsonl).  Callers with pinned buffers (doppler_b200_host_alloc / _register) skip this.
-void staged_copy(void* dst, const void* src, size_t bytes)
+// Staging copies between the caller's pageable buffers and the pinned slots.  One thread moves ~10 GB/s, a fifth of what
+// PCIe takes, so large copies are spread over a small pool of persistent worker threads (created on the first large copy;
+// round 1 spawned up to 4 threads per copy: 1.0-1.5 Gsample/s end to end, profiles/r01_percall_latency.jsonl).  Callers
+// with pinned buffers (doppler_b200_host_alloc / _register) never come here.
+class CopyPool {
+public:
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            quit_ = true;
+        }
+        cv_work_.notify_all();
+        for (std::thread& t : workers_) t.join();
+    }
+
+    void copy(void* dst, const void* src, size_t bytes)
+    {
+        constexpr size_t kPerThread = 2u << 20;
+        const unsigned hw = std::thread::hardware_concurrency();
+        const size_t want = std::min<size_t>({bytes / kPerThread, (size_t)(hw > 2 ? hw / 2 : 1), (size_t)kMaxThreads});
+        if (want <= 1) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        while (workers_.size() + 1 < want) {
+            const size_t id = workers_.size();
+            workers_.emplace_back([this, id] { run(id); });
+        }
+        const size_t parts = workers_.size() + 1;
+        const size_t part = (bytes / parts + 4095) & ~(size_t)4095;
+        {
+            std::lock_guard<std::mutex> g(m_);
+            dst_ = static_cast<char*>(dst);
+            src_ = static_cast<const char*>(src);
+            bytes_ = bytes;
+            part_ = part;
+            pending_ = (int)workers_.size();
+            generation_++;
+        }
+        cv_work_.notify_all();
+        memcpy(dst, src, std::min(part, bytes));   // the caller takes part 0
+        std::unique_lock<std::mutex> g(m_);
+        cv_done_.wait(g, [&] { return pending_ == 0; });
+    }
+
+private:
+    static constexpr int kMaxThreads = 8;
+    void run(size_t id)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            char* dst;
+            const char* src;
+            size_t bytes, part;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_work_.wait(g, [&] { return quit_ || generation_ != seen; });
+                if (quit_) return;
+                seen = generation_;
+                dst = dst_, src = src_, bytes = bytes_, part = part_;
+            }
+            const size_t off = (id + 1) * part;
+            if (off < bytes) memcpy(dst + off, src + off, std::min(part, bytes - off));
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0) cv_done_.notify_one();
+            }
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> workers_;
+    char* dst_ = nullptr;
+    const char* src_ = nullptr;
+    size_t bytes_ = 0, part_ = 0;
+    int pending_ = 0;
+    uint64_t generation_ = 0;
+    bool quit_ = false;
+};
+
+void staged_copy(doppler_b200_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
-    constexpr size_t kPerThread = 4u << 20;
-    const unsigned hw = std::thread::hardware_concurrency();
-    const size_t nthreads = std::min<size_t>({bytes / kPerThread, (size_t)(hw ? hw : 1), (size_t)4});
-    if (nthreads <= 1) {
-        memcpy(dst, src, bytes);
-        return;
-    }
-    const size_t part = (bytes / nthreads + 63) & ~(size_t)63;
-    std::vector<std::thread> th;
-    for (size_t t = 1; t < nthreads; t++) {
-        const size_t off = t * part, len = off >= bytes ? 0 : std::min(part, bytes - off);
-        if (len) th.emplace_back([=] { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
-    }
-    memcpy(dst, src, std::min(part, bytes));
-    for (std::thread& x : th) x.join();
+    if (!ctx->copy_pool) ctx->copy_pool = new CopyPool;
+    static_cast<CopyPool*>(ctx->copy_pool)->copy(dst, src, bytes);
 }
 
 int retire_slot(doppler_b200_ctx* ctx, Slot& sl)
 {
     if (!sl.busy) return DOPPLER_B200_OK;
     CUDA_TRY(ctx, cudaEventSynchronize(sl.done));
-    if (sl.user_out) staged_copy(sl.user_out, sl.h_out, sl.user_out_bytes);
+    if (sl.user_out) staged_copy(ctx, sl.user_out, sl.h_out, sl.user_out_bytes);
     sl.user_out = nullptr;
     sl.busy = false;
     return DOPPLER_B200_OK;
@@ -869,7 +938,7 @@ int mix_host_run(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int i
         if (rc) return rc;
         const char* src = static_cast<const char*>(in) + k * ibps;
         if (!in_pinned) {
-            staged_copy(sl.h_in, src, n * ibps);
+            staged_copy(ctx, sl.h_in, src, n * ibps);
             src = static_cast<const char*>(sl.h_in);
         }
         CUDA_TRY(ctx, cudaMemcpyAsync(sl.d_in, src, n * ibps, cudaMemcpyHostToDevice, sl.stream));
@@ -1008,6 +1077,7 @@ void doppler_b200_destroy(doppler_b200_ctx* ctx)
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
+    delete static_cast<CopyPool*>(ctx->copy_pool);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->done_flag) cudaFreeHost(ctx->done_flag);
     if (ctx->done_counter) cudaFree(ctx->done_counter);

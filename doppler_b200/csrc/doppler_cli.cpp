@@ -584,11 +584,19 @@ int main(int argc, char** argv)
     }
 
     // ---- const mode and track replay: chunked pump, reader / GPU / writer overlapped ----
-    for (Chunk& c : chunks)   // pin in place (the reader may already be filling them); unpinned still works, slower
-        if (doppler_b200_host_register(c.in, in_cap) != 0 || doppler_b200_host_register(c.out, out_cap) != 0)
-            INFO("could not pin the chunk buffers: %s", doppler_b200_last_error(ctx));
-    if (getenv("DOPPLER_STATS"))
-        fprintf(stderr, "{\"startup_ms_context\": %.1f, \"startup_ms_pinned_buffers\": %.1f}\n", ms_create, since_start_ms() - ms_create);
+    // The chunk buffers are pinned in place (the reader may already be filling them) only once a FULL chunk has arrived,
+    // i.e. when the producer is fast enough for the copies to matter: pinning 6 x 32 MiB costs tens of milliseconds, more
+    // than the whole job when stdin is a second of a 256 ksps stream (BASELINE configs[0]) or a live radio.
+    bool pinned = false;
+    auto pin_chunks = [&] {
+        const double t0 = since_start_ms();
+        for (Chunk& c : chunks)
+            if (doppler_b200_host_register(c.in, in_cap) != 0 || doppler_b200_host_register(c.out, out_cap) != 0)
+                INFO("could not pin the chunk buffers: %s", doppler_b200_last_error(ctx));
+        pinned = true;
+        if (getenv("DOPPLER_STATS")) fprintf(stderr, "{\"pinned_buffers_ms\": %.1f}\n", since_start_ms() - t0);
+    };
+    if (getenv("DOPPLER_STATS")) fprintf(stderr, "{\"startup_ms_context\": %.1f}\n", ms_create);
 
     std::thread writer([&] {
         for (;;) {
@@ -612,6 +620,7 @@ int main(int argc, char** argv)
     for (;;) {
         const int i = filled_q.pop();
         Chunk& c = chunks[i];
+        if (!pinned && c.in_len == in_cap) pin_chunks();
         // The reference asserts len % bps == 0 in the converter of the short final block
         // (dsp.rs:87,103) AFTER every earlier block has been written: mix the whole samples of
         // the full blocks, then report the panic.
@@ -696,8 +705,10 @@ int main(int argc, char** argv)
     }
     if (exit_code == 101) fprintf(stderr, "thread 'main' panicked at 'assertion failed: inbuf.len() %% %zu == 0', src/dsp.rs\n", ibps);
     for (Chunk& c : chunks) {
-        doppler_b200_host_unregister(c.in);
-        doppler_b200_host_unregister(c.out);
+        if (pinned) {
+            doppler_b200_host_unregister(c.in);
+            doppler_b200_host_unregister(c.out);
+        }
         free(c.in);
         free(c.out);
     }
