@@ -13,6 +13,7 @@ from .dsp import (  # noqa: F401
     DopplerError,
     Mixer,
     MultiMixer,
+    Decimator,
     convert_iqf32_to_complex,
     convert_iqi16_to_complex,
     samplenum_advance,
@@ -21,7 +22,7 @@ from .dsp import (  # noqa: F401
 )
 
 __all__ = [
-    "dsp", "Mixer", "MultiMixer", "DopplerError", "I16", "F32", "BUFFER_SIZE",
+    "dsp", "Mixer", "MultiMixer", "Decimator", "DopplerError", "I16", "F32", "BUFFER_SIZE",
     "convert_iqi16_to_complex", "convert_iqf32_to_complex", "shift_frequency",
     "samplenum_advance", "samplenum_advance_blocks",
 ]

@@ -37,6 +37,20 @@ SIGNATURES = {
     "doppler_b200_mix_blocks": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint32, u32p,
                                                ctypes.c_void_p, ctypes.c_size_t, szp]),
+    "doppler_b200_decim_create": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p)]),
+    "doppler_b200_decim_destroy": (None, [ctypes.c_void_p]),
+    "doppler_b200_decim_reset": (ctypes.c_int, [ctypes.c_void_p]),
+    "doppler_b200_decim_position": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "doppler_b200_mix_decimate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_float, ctypes.c_uint32, u32p, ctypes.c_void_p, ctypes.c_size_t, szp]),
+    "doppler_b200_mix_blocks_decimate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                                        ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint32, u32p,
+                                                        ctypes.c_void_p, ctypes.c_size_t, szp]),
+    "doppler_b200_mix_decimate_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                                     ctypes.c_float, ctypes.c_uint32, u32p, ctypes.c_void_p, ctypes.c_size_t, szp, ctypes.c_void_p]),
+    "doppler_b200_mix_blocks_decimate_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint32, u32p,
+                                                            ctypes.c_void_p, ctypes.c_size_t, szp, ctypes.c_void_p]),
     "doppler_b200_mix_dev": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_float, ctypes.c_uint32, u32p, ctypes.c_void_p, ctypes.c_size_t,
                                             ctypes.c_void_p]),

@@ -1230,6 +1230,329 @@ int doppler_b200_pipeline_probe(doppler_b200_ctx* ctx, const void* in, size_t in
     return mix_host(ctx, in, n, intype, outtype, &zero, 1, 0, 1, &sn, out, /*copy_only=*/true);
 }
 
+// ---- fused downstream stage: mix + decimating FIR ---------------------------
+}  // extern "C"
+
+struct doppler_b200_decim {
+    doppler_b200_ctx* ctx = nullptr;
+    uint32_t ntaps = 0, M = 0;
+    float* d_taps = nullptr;
+    float2* d_hist[2] = {nullptr, nullptr};   // history ping-pong (ntaps-1 mixed samples)
+    int cur = 0;
+    uint64_t pos = 0;                          // stream position of the next input sample
+    DevPiece* d_pieces = nullptr;              // piece list of the call in flight (when it does not fit the kernel parameters)
+    size_t pieces_cap = 0;
+    cudaEvent_t hist_ready = nullptr;          // the history of the latest call has been written
+    cudaStream_t hist_stream = nullptr;
+    bool hist_event_valid = false;
+};
+
+namespace {
+
+constexpr uint32_t kDecimMaxTaps = 4096;
+constexpr uint32_t kDecimStageSlots = 5120;   // mixed samples staged per CTA step (40 KB)
+
+using DecimKernel = void (*)(const dmix::DecimArgs);
+
+// One device-resident call of the fused stage: `runs` over n samples at d_in; outputs to d_out.  Asynchronous on `s`.
+int decimate_launch(doppler_b200_decim* dec, const void* d_in, uint64_t n, int intype, int outtype, const std::vector<dplan::Run>& runs,
+                    uint32_t* samplenum, void* d_out, uint64_t* nout_ret, cudaStream_t s)
+{
+    doppler_b200_ctx* ctx = dec->ctx;
+    *nout_ret = 0;
+    if (n == 0) return DOPPLER_B200_OK;
+    if (n > kLaunchMaxSamples) return fail(ctx, DOPPLER_B200_EINVAL, "one fused mix + decimate call is limited to 2^30 samples");
+    std::vector<dplan::Piece> pieces;
+    uint32_t sn_after = *samplenum;
+    ctx->planner.plan(runs, 0, &sn_after, &pieces);
+    std::vector<DevPiece> dev;
+    std::vector<const dplan::Piece*> src;
+    clip_pieces(pieces, 0, n, 1, &dev, &src);
+    if (ctx->tables_event_valid && s != ctx->tables_stream) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->tables_ready, 0));
+    for (size_t i = 0; i < dev.size(); i++)
+        if (dev[i].period) {
+            int rc = get_table(ctx, dev[i].r, dev[i].period, src[i]->k_end - src[i]->k_begin, s, &dev[i].tab);
+            if (rc) return rc;
+        }
+    for (DevPiece& d : dev) {   // a recycled arena invalidates offsets taken earlier in this call
+        if (d.tab == dmix::kNoTab) continue;
+        uint32_t key;
+        memcpy(&key, &d.r, 4);
+        auto it = ctx->tables.find(key);
+        d.tab = (it != ctx->tables.end() && it->second.period == d.period) ? it->second.off : dmix::kNoTab;
+    }
+    dmix::DecimArgs a;
+    memset(&a, 0, sizeof a);
+    a.mix.in = d_in;
+    a.mix.tables = ctx->arena;
+    a.mix.nsamples = (uint32_t)n;
+    a.mix.npieces = (uint32_t)dev.size();
+    if (dev.size() <= (size_t)dmix::kInlinePieces) {
+        for (size_t i = 0; i < dev.size(); i++) a.mix.inl[i] = dev[i];
+    } else {
+        if (dec->pieces_cap < dev.size()) {
+            if (dec->d_pieces) CUDA_TRY(ctx, cudaFree(dec->d_pieces));
+            dec->d_pieces = nullptr;
+            dec->pieces_cap = 0;
+            CUDA_TRY(ctx, cudaMalloc(&dec->d_pieces, dev.size() * 2 * sizeof(DevPiece)));
+            dec->pieces_cap = dev.size() * 2;
+        }
+        // pageable source: the copy is staged before the call returns, so `dev` may go out of scope
+        CUDA_TRY(ctx, cudaMemcpyAsync(dec->d_pieces, dev.data(), dev.size() * sizeof(DevPiece), cudaMemcpyHostToDevice, s));
+        a.mix.pieces = dec->d_pieces;
+    }
+    // the previous call's history must have landed (it may have been written on another slot's stream)
+    if (dec->hist_event_valid && s != dec->hist_stream) CUDA_TRY(ctx, cudaStreamWaitEvent(s, dec->hist_ready, 0));
+    const uint32_t M = dec->M;
+    a.out = d_out;
+    a.hist = dec->d_hist[dec->cur];
+    a.hist_next = dec->d_hist[dec->cur ^ 1];
+    a.taps = dec->d_taps;
+    a.ntaps = dec->ntaps;
+    a.M = M;
+    const uint64_t i0 = (M - dec->pos % M) % M;
+    a.first_out = (uint32_t)i0;
+    const uint64_t nout = i0 < n ? (n - i0 + M - 1) / M : 0;
+    a.nout = (uint32_t)nout;
+    a.skew = (M % 2 == 0) ? 1u : 0u;
+    // outputs per CTA step: as many as the staging area holds, at most one per thread
+    const uint64_t usable = a.skew ? (uint64_t)kDecimStageSlots * M / (M + 1) - 1 : kDecimStageSlots;
+    uint64_t ot = usable > dec->ntaps ? (usable - dec->ntaps) / M + 1 : 1;
+    ot = std::max<uint64_t>(1, std::min<uint64_t>(ot, dmix::kDecimThreads));
+    a.out_per_cta = (uint32_t)ot;
+    const uint64_t count = (ot - 1) * M + dec->ntaps;
+    const size_t slots = a.skew ? count + count / M + 2 : count;
+    const size_t smem = ((dec->ntaps * 4 + 15) & ~(size_t)15) + slots * sizeof(float2);
+    static const DecimKernel kern[2][2] = {{dmix::mix_decimate_kernel<0, 0>, dmix::mix_decimate_kernel<0, 1>},
+                                           {dmix::mix_decimate_kernel<1, 0>, dmix::mix_decimate_kernel<1, 1>}};
+    if (nout) {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((nout + ot - 1) / ot, (uint64_t)ctx->sm_count * 8);
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kern[intype][outtype], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern[intype][outtype]<<<grid, dmix::kDecimThreads, smem, s>>>(a);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    if (dec->ntaps > 1) {
+        const uint32_t hgrid = (dec->ntaps - 1 + dmix::kDecimThreads - 1) / dmix::kDecimThreads;
+        if (intype == DOPPLER_B200_I16)
+            dmix::decim_history_kernel<0><<<hgrid, dmix::kDecimThreads, 0, s>>>(a);
+        else
+            dmix::decim_history_kernel<1><<<hgrid, dmix::kDecimThreads, 0, s>>>(a);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaEventRecord(dec->hist_ready, s));
+        dec->hist_event_valid = true;
+        dec->hist_stream = s;
+        dec->cur ^= 1;
+    }
+    dec->pos += n;
+    *samplenum = sn_after;
+    *nout_ret = nout;
+    return DOPPLER_B200_OK;
+}
+
+int decim_check(doppler_b200_decim* dec, const void* in, size_t in_len, int intype, int outtype, uint32_t* samplenum, void* out, size_t out_cap,
+                uint64_t* n, uint64_t* nout)
+{
+    if (!dec) return DOPPLER_B200_EINVAL;
+    doppler_b200_ctx* ctx = dec->ctx;
+    if (!valid_type(intype) || !valid_type(outtype)) return fail(ctx, DOPPLER_B200_EINVAL, "unknown IQ data type");
+    if (!samplenum) return fail(ctx, DOPPLER_B200_EINVAL, "samplenum is NULL");
+    const size_t ibps = bytes_per_sample(intype);
+    if (in_len % ibps != 0) return fail(ctx, DOPPLER_B200_EALIGN, "input length %zu is not a multiple of %zu (dsp.rs assert)", in_len, ibps);
+    *n = in_len / ibps;
+    const uint64_t i0 = (dec->M - dec->pos % dec->M) % dec->M;
+    *nout = i0 < *n ? (*n - i0 + dec->M - 1) / dec->M : 0;
+    if (*n && !in) return fail(ctx, DOPPLER_B200_EINVAL, "NULL buffer");
+    if (*nout && !out) return fail(ctx, DOPPLER_B200_EINVAL, "NULL buffer");
+    if (*nout * bytes_per_sample(outtype) > out_cap)
+        return fail(ctx, DOPPLER_B200_ECAP, "output capacity %zu < %llu bytes needed", out_cap, (unsigned long long)(*nout * bytes_per_sample(outtype)));
+    return DOPPLER_B200_OK;
+}
+
+std::vector<dplan::Run> decim_runs(const float* shifts, size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint64_t k, uint64_t n)
+{
+    if (nblocks <= 1 || block_samples == 0) return {dplan::Run{n, dplan::ratio(shifts[0], samplerate)}};
+    const size_t b0 = (size_t)(k / block_samples);
+    return dplan::runs_from_blocks(shifts + b0, nblocks - b0, block_samples, samplerate, n);
+}
+
+// Host buffers: the chunk pipeline of mix_host (H2D / kernels / D2H of neighbouring chunks overlap across the slots' streams;
+// the history hand-over between chunks is ordered through dec->hist_ready).
+int decimate_host(doppler_b200_decim* dec, const void* in, uint64_t n, int intype, int outtype, const float* shifts, size_t nblocks,
+                  uint64_t block_samples, uint32_t samplerate, uint32_t* samplenum, void* out, size_t* out_len)
+{
+    doppler_b200_ctx* ctx = dec->ctx;
+    const size_t ibps = bytes_per_sample(intype), obps = bytes_per_sample(outtype);
+    uint64_t chunk = kHostChunkBytes / ibps;
+    if (block_samples && nblocks > 1) chunk = std::max<uint64_t>(block_samples, chunk / block_samples * block_samples);
+    const bool in_pinned = is_pinned(in), out_pinned = is_pinned(out);
+    uint32_t sn = *samplenum;
+    size_t written = 0;
+    int c = 0;
+    for (uint64_t k = 0; k < n; k += chunk, c++) {
+        const uint64_t m = std::min(chunk, n - k);
+        Slot& sl = ctx->slots[c % kSlots];
+        int rc = retire_slot(ctx, sl);
+        if (rc) return rc;
+        rc = ensure_slot(ctx, sl, std::min<uint64_t>(chunk, n) * ibps, (std::min<uint64_t>(chunk, n) / dec->M + 2) * obps);
+        if (rc) return rc;
+        const char* src = static_cast<const char*>(in) + k * ibps;
+        if (!in_pinned) {
+            staged_copy(ctx, sl.h_in, src, m * ibps);
+            src = static_cast<const char*>(sl.h_in);
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(sl.d_in, src, m * ibps, cudaMemcpyHostToDevice, sl.stream));
+        uint64_t nout = 0;
+        rc = decimate_launch(dec, sl.d_in, m, intype, outtype, decim_runs(shifts, nblocks, block_samples, samplerate, k, m), &sn, sl.d_out, &nout,
+                             sl.stream);
+        if (rc) return rc;
+        char* dst = static_cast<char*>(out) + written;
+        if (nout) {
+            if (out_pinned) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(dst, sl.d_out, nout * obps, cudaMemcpyDeviceToHost, sl.stream));
+                sl.user_out = nullptr;
+            } else {
+                CUDA_TRY(ctx, cudaMemcpyAsync(sl.h_out, sl.d_out, nout * obps, cudaMemcpyDeviceToHost, sl.stream));
+                sl.user_out = dst;
+                sl.user_out_bytes = nout * obps;
+            }
+        }
+        CUDA_TRY(ctx, cudaEventRecord(sl.done, sl.stream));
+        sl.busy = true;
+        written += nout * obps;
+    }
+    for (int i = 0; i < kSlots; i++) {
+        int rc = retire_slot(ctx, ctx->slots[i]);
+        if (rc) return rc;
+    }
+    *samplenum = sn;
+    if (out_len) *out_len = written;
+    return DOPPLER_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int doppler_b200_decim_create(doppler_b200_ctx* ctx, const float* taps, uint32_t ntaps, uint32_t decimation, doppler_b200_decim** out)
+{
+    if (!ctx || !out) return DOPPLER_B200_EINVAL;
+    *out = nullptr;
+    if (!taps || ntaps == 0 || ntaps > kDecimMaxTaps || decimation == 0 || decimation > (1u << 20))
+        return fail(ctx, DOPPLER_B200_EINVAL, "decimator: 1..%u taps, decimation 1..2^20", kDecimMaxTaps);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    doppler_b200_decim* d = new (std::nothrow) doppler_b200_decim;
+    if (!d) return DOPPLER_B200_ENOMEM;
+    d->ctx = ctx;
+    d->ntaps = ntaps;
+    d->M = decimation;
+    const size_t hb = std::max<size_t>(ntaps - 1, 1) * sizeof(float2);
+    cudaError_t e = cudaMalloc(&d->d_taps, ntaps * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d->d_taps, taps, ntaps * sizeof(float), cudaMemcpyHostToDevice);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaMalloc(&d->d_hist[i], hb);
+        if (e == cudaSuccess) e = cudaMemset(d->d_hist[i], 0, hb);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->hist_ready, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        fail(ctx, DOPPLER_B200_ECUDA, "decimator setup failed: %s", cudaGetErrorString(e));
+        doppler_b200_decim_destroy(d);
+        return DOPPLER_B200_ECUDA;
+    }
+    *out = d;
+    return DOPPLER_B200_OK;
+}
+
+void doppler_b200_decim_destroy(doppler_b200_decim* d)
+{
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    cudaDeviceSynchronize();
+    if (d->d_taps) cudaFree(d->d_taps);
+    for (float2* h : d->d_hist)
+        if (h) cudaFree(h);
+    if (d->d_pieces) cudaFree(d->d_pieces);
+    if (d->hist_ready) cudaEventDestroy(d->hist_ready);
+    delete d;
+}
+
+int doppler_b200_decim_reset(doppler_b200_decim* d)
+{
+    if (!d) return DOPPLER_B200_EINVAL;
+    CUDA_TRY(d->ctx, cudaSetDevice(d->ctx->device));
+    CUDA_TRY(d->ctx, cudaDeviceSynchronize());
+    const size_t hb = std::max<size_t>(d->ntaps - 1, 1) * sizeof(float2);
+    for (float2* h : d->d_hist) CUDA_TRY(d->ctx, cudaMemset(h, 0, hb));
+    d->pos = 0;
+    d->cur = 0;
+    d->hist_event_valid = false;
+    return DOPPLER_B200_OK;
+}
+
+uint64_t doppler_b200_decim_position(const doppler_b200_decim* d) { return d ? d->pos : 0; }
+
+int doppler_b200_mix_blocks_decimate(doppler_b200_decim* dec, const void* in, size_t in_len, int intype, int outtype,
+                                     const float* shift_hz_per_block, size_t nblocks, size_t block_bytes, uint32_t samplerate,
+                                     uint32_t* samplenum, void* out, size_t out_cap, size_t* out_len)
+{
+    uint64_t n = 0, nout = 0, bs = 0;
+    int rc = decim_check(dec, in, in_len, intype, outtype, samplenum, out, out_cap, &n, &nout);
+    if (rc) return rc;
+    if (out_len) *out_len = 0;
+    if (n == 0) return DOPPLER_B200_OK;
+    rc = check_blocks(dec->ctx, in_len, intype, shift_hz_per_block, nblocks, block_bytes, &bs);
+    if (rc) return rc;
+    CUDA_TRY(dec->ctx, cudaSetDevice(dec->ctx->device));
+    const uint64_t pos0 = dec->pos;
+    const int cur0 = dec->cur;
+    rc = decimate_host(dec, in, n, intype, outtype, shift_hz_per_block, nblocks, bs, samplerate, samplenum, out, out_len);
+    if (rc) {   // nothing of a failed call may stay in flight or in the state
+        const std::string keep = dec->ctx->err;
+        abandon_slots(dec->ctx);
+        dec->ctx->err = keep;
+        dec->pos = pos0;
+        dec->cur = cur0;
+    }
+    return rc;
+}
+
+int doppler_b200_mix_decimate(doppler_b200_decim* dec, const void* in, size_t in_len, int intype, int outtype, float shift_hz,
+                              uint32_t samplerate, uint32_t* samplenum, void* out, size_t out_cap, size_t* out_len)
+{
+    const size_t whole = in_len ? in_len : 1;
+    return doppler_b200_mix_blocks_decimate(dec, in, in_len, intype, outtype, &shift_hz, 1, (whole + 7) / 8 * 8, samplerate, samplenum, out, out_cap,
+                                            out_len);
+}
+
+int doppler_b200_mix_blocks_decimate_dev(doppler_b200_decim* dec, const void* d_in, size_t in_len, int intype, int outtype,
+                                         const float* shift_hz_per_block, size_t nblocks, size_t block_bytes, uint32_t samplerate,
+                                         uint32_t* samplenum, void* d_out, size_t out_cap, size_t* out_len, void* stream)
+{
+    uint64_t n = 0, nout = 0, bs = 0;
+    int rc = decim_check(dec, d_in, in_len, intype, outtype, samplenum, d_out, out_cap, &n, &nout);
+    if (rc) return rc;
+    if (out_len) *out_len = 0;
+    if (n == 0) return DOPPLER_B200_OK;
+    rc = check_blocks(dec->ctx, in_len, intype, shift_hz_per_block, nblocks, block_bytes, &bs);
+    if (rc) return rc;
+    if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail(dec->ctx, DOPPLER_B200_EINVAL, "device buffers must be 16-byte aligned");
+    CUDA_TRY(dec->ctx, cudaSetDevice(dec->ctx->device));
+    uint64_t got = 0;
+    rc = decimate_launch(dec, d_in, n, intype, outtype, decim_runs(shift_hz_per_block, nblocks, bs, samplerate, 0, n), samplenum, d_out, &got,
+                         stream ? (cudaStream_t)stream : dec->ctx->stream);
+    if (rc == DOPPLER_B200_OK && out_len) *out_len = got * bytes_per_sample(outtype);
+    return rc;
+}
+
+int doppler_b200_mix_decimate_dev(doppler_b200_decim* dec, const void* d_in, size_t in_len, int intype, int outtype, float shift_hz,
+                                  uint32_t samplerate, uint32_t* samplenum, void* d_out, size_t out_cap, size_t* out_len, void* stream)
+{
+    const size_t whole = in_len ? in_len : 1;
+    return doppler_b200_mix_blocks_decimate_dev(dec, d_in, in_len, intype, outtype, &shift_hz, 1, (whole + 7) / 8 * 8, samplerate, samplenum, d_out,
+                                                out_cap, out_len, stream);
+}
+
 // ---- the reference's three functions, one to one ---------------------------------------------
 
 int doppler_b200_shift_frequency(doppler_b200_ctx* ctx, const float* inbuf, size_t nsamples, uint32_t* samplenum,

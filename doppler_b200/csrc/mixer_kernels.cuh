@@ -1262,6 +1262,100 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused downstream stage (not in the reference): mix, then a decimate-by-M FIR, in one pass.
+//   y[k] = the mixer's Complex<f32> result for stream sample k (exactly the arithmetic above), y[k] = 0 before the stream
+//   z[m] = sum over t = 0 .. ntaps-1, in that order, of h[t] * y[m*M - t], one fused multiply-add per step (fmaf), re / im apart
+// (specification: the definition in include/doppler_b200.h, restated on the CPU by the test checker).  The output is 1/M of the stream, so for host callers the
+// device -> host copy -- half of the PCIe traffic of an i16 -> i16 mix -- shrinks by M.  A CTA stages the mixed samples its
+// outputs need in shared memory (for even M skewed by one slot per M samples, so that the lanes' reads at stride M fall in
+// distinct banks), then every thread accumulates one output.
+struct DecimArgs {
+    MixArgs mix;             // in, pieces, tables of this call (out unused)
+    void* out;               // decimated output (outtype)
+    const float2* hist;      // the ntaps-1 mixed samples before this call's first sample, oldest first
+    float2* hist_next;       // (history pass) the ntaps-1 mixed samples before the NEXT call's first sample
+    const float* taps;
+    uint32_t ntaps, M;
+    uint32_t first_out;      // call-relative index of the first sample whose stream position is a multiple of M
+    uint32_t nout;           // outputs of this call
+    uint32_t out_per_cta;    // outputs per CTA step
+    uint32_t skew;           // 1: staged sample j lives at slot j + j / M
+};
+constexpr int kDecimThreads = 256;
+
+// the mixer's result for call-relative sample i (any piece, table or direct evaluation)
+template <int IN>
+__device__ __forceinline__ float2 mix_one(const MixArgs& a, uint32_t i, uint32_t& pi, DevPiece& p)
+{
+    if (i >= p.k_end || i < p.k_begin) {
+        pi = find_piece(a, i < p.k_begin ? 0u : pi, i);
+        p = get_piece(a, pi);
+    }
+    const uint32_t n = piece_samplenum(p, i - p.k_begin);
+    const float2 ph = p.tab != kNoTab ? __ldg(a.tables + p.tab + (n - 1u)) : phasor(p.r, n);
+    return cmul_unfused(load_sample<IN>(a.in, i), ph);
+}
+
+template <int IN, int OUT>
+__global__ void __launch_bounds__(kDecimThreads) mix_decimate_kernel(const __grid_constant__ DecimArgs d)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* taps_s = reinterpret_cast<float*>(smem);
+    float2* y_s = reinterpret_cast<float2*>(smem + ((d.ntaps * 4 + 15) & ~15u));
+    const uint32_t nh = d.ntaps - 1u, M = d.M, OT = d.out_per_cta;
+    for (uint32_t t = threadIdx.x; t < d.ntaps; t += kDecimThreads) taps_s[t] = d.taps[t];
+    uint32_t pi = 0;
+    DevPiece p = get_piece(d.mix, 0);
+    for (uint32_t ob = blockIdx.x * OT; ob < d.nout; ob += gridDim.x * OT) {
+        const uint32_t ocount = d.nout - ob < OT ? d.nout - ob : OT;
+        // staged slot j holds call-relative sample i0 + j, i0 = first_out + ob*M - nh (may be negative: history)
+        const int64_t i0 = (int64_t)d.first_out + (int64_t)ob * M - (int64_t)nh;
+        const uint32_t count = (ocount - 1u) * M + d.ntaps;
+        __syncthreads();   // the previous step's readers are done (and the taps are staged)
+        for (uint32_t j = threadIdx.x; j < count; j += kDecimThreads) {
+            const int64_t i = i0 + (int64_t)j;
+            const float2 y = i < 0 ? d.hist[(int64_t)nh + i] : mix_one<IN>(d.mix, (uint32_t)i, pi, p);
+            y_s[d.skew ? j + j / M : j] = y;
+        }
+        __syncthreads();
+        if (threadIdx.x < ocount) {
+            uint32_t j = nh + threadIdx.x * M;            // slot index (unskewed) of sample m*M
+            uint32_t rem = j % M;
+            uint32_t slot = d.skew ? j + j / M : j;
+            float re = 0.0f, im = 0.0f;
+            for (uint32_t t = 0; t < d.ntaps; t++) {
+                const float2 y = y_s[slot];
+                const float h = taps_s[t];
+                re = __fmaf_rn(h, y.x, re);
+                im = __fmaf_rn(h, y.y, im);
+                // one sample back; crossing a multiple of M skips the skew slot
+                if (rem == 0u) {
+                    rem = M - 1u;
+                    slot -= 1u + d.skew;
+                } else {
+                    rem -= 1u;
+                    slot -= 1u;
+                }
+            }
+            store_sample<OUT>(d.out, ob + threadIdx.x, make_float2(re, im));
+        }
+    }
+}
+
+// History pass: the last ntaps-1 mixed samples of the stream after this call (older ones come from the previous history).
+template <int IN>
+__global__ void __launch_bounds__(kDecimThreads) decim_history_kernel(const __grid_constant__ DecimArgs d)
+{
+    const uint32_t nh = d.ntaps - 1u;
+    uint32_t pi = 0;
+    DevPiece p = get_piece(d.mix, 0);
+    for (uint32_t j = blockIdx.x * kDecimThreads + threadIdx.x; j < nh; j += gridDim.x * kDecimThreads) {
+        const int64_t i = (int64_t)d.mix.nsamples - (int64_t)nh + (int64_t)j;
+        d.hist_next[j] = i < 0 ? d.hist[(int64_t)nh + i] : mix_one<IN>(d.mix, (uint32_t)i, pi, p);
+    }
+}
+
 // Phasor table of one shift: entry j (0 <= j < period + kTabPad) = phasor(r, (j mod period) + 1).
 __global__ void __launch_bounds__(kThreads) build_phasor_table_kernel(float2* tab, float r, uint32_t period, uint32_t entries)
 {

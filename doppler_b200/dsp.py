@@ -152,6 +152,65 @@ class Mixer:
         return s, c
 
 
+class Decimator:
+    """Mix + decimate-by-M FIR in one pass (include/doppler_b200.h: doppler_b200_decim_*; not in the reference).
+    Carries the FIR history and the stream position across calls; the caller carries samplenum."""
+
+    def __init__(self, mixer, taps, decimation):
+        self._lib = mixer._lib
+        self._mixer = mixer
+        h = np.ascontiguousarray(taps, dtype=np.float32)
+        self._d = ctypes.c_void_p()
+        self.decimation = int(decimation)
+        mixer._check(self._lib.doppler_b200_decim_create(mixer._ctx, _ptr(h), h.size, int(decimation), ctypes.byref(self._d)))
+
+    def close(self):
+        if getattr(self, "_d", None):
+            self._lib.doppler_b200_decim_destroy(self._d)
+            self._d = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._mixer._check(self._lib.doppler_b200_decim_reset(self._d))
+
+    @property
+    def position(self):
+        return int(self._lib.doppler_b200_decim_position(self._d))
+
+    def mix(self, inbuf, intype, outtype, shift_hz, samplerate, samplenum=0):
+        a = _as_bytes_array(inbuf)
+        out = np.empty((a.size // _BPS[intype] // self.decimation + 2) * _BPS[outtype], dtype=np.uint8)
+        sn = ctypes.c_uint32(samplenum)
+        n = ctypes.c_size_t(0)
+        self._mixer._check(self._lib.doppler_b200_mix_decimate(self._d, _ptr(a), a.size, intype, outtype, ctypes.c_float(shift_hz),
+                                                               int(samplerate), ctypes.byref(sn), _ptr(out), out.size, ctypes.byref(n)))
+        return out[:n.value], sn.value
+
+    def mix_blocks(self, inbuf, intype, outtype, shifts_hz, samplerate, samplenum=0, block_bytes=BUFFER_SIZE):
+        a = _as_bytes_array(inbuf)
+        sh = np.ascontiguousarray(shifts_hz, dtype=np.float32)
+        out = np.empty((a.size // _BPS[intype] // self.decimation + 2) * _BPS[outtype], dtype=np.uint8)
+        sn = ctypes.c_uint32(samplenum)
+        n = ctypes.c_size_t(0)
+        self._mixer._check(self._lib.doppler_b200_mix_blocks_decimate(self._d, _ptr(a), a.size, intype, outtype, _ptr(sh), sh.size, block_bytes,
+                                                                      int(samplerate), ctypes.byref(sn), _ptr(out), out.size, ctypes.byref(n)))
+        return out[:n.value], sn.value
+
+    def mix_dev(self, d_in, in_len, intype, outtype, shift_hz, samplerate, samplenum, d_out, out_cap, stream=None):
+        """Device buffers; returns (bytes written, samplenum)."""
+        sn = ctypes.c_uint32(samplenum)
+        n = ctypes.c_size_t(0)
+        self._mixer._check(self._lib.doppler_b200_mix_decimate_dev(self._d, ctypes.c_void_p(d_in), in_len, intype, outtype, ctypes.c_float(shift_hz),
+                                                                   int(samplerate), ctypes.byref(sn), ctypes.c_void_p(d_out), out_cap, ctypes.byref(n),
+                                                                   ctypes.c_void_p(stream or 0)))
+        return n.value, sn.value
+
+
 class MultiMixer:
     """A group of contexts, one per GPU of the box (include/doppler_b200.h: doppler_b200_multi_create).  One stream is
     cut into contiguous time slices on pump-block boundaries, slice d goes to device d; no collective."""

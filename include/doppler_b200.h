@@ -133,6 +133,35 @@ int doppler_b200_mix_blocks(doppler_b200_ctx* ctx, const void* in, size_t in_len
                             const float* shift_hz_per_block, size_t nblocks, size_t block_bytes, uint32_t samplerate,
                             uint32_t* samplenum, void* out, size_t out_cap, size_t* out_len);
 
+/* ---- fused downstream stage: mix + decimate-by-M FIR (not in the reference) ---------------- */
+
+/* The usual next block after `doppler` in an SDR pipe (README.md:53 feeds a demodulator) is a low-pass
+ * decimator; fusing it after the mixer keeps the mixed stream on the chip and shrinks the output -- and for
+ * host callers the device -> host copy -- by M.  Definition (oracle/doppler_oracle.c: oracle_mix_decimate):
+ *   y[k] = the mixer's Complex<f32> result for stream sample k (the reference's arithmetic, dsp.rs:117-134)
+ *   z[m] = sum over t = 0 .. ntaps-1, in that order, of taps[t] * y[m*M - t]   (y = 0 before the stream;
+ *          one fused multiply-add in f32 per step, real and imaginary parts separately)
+ *   out  = z as f32 pairs, or (z * 32767.0) as i16 like main.rs:73-87
+ * Output m is produced by the call that supplies input sample m*M; the object carries the last ntaps-1 mixed
+ * samples and the stream position across calls, the caller carries samplenum as everywhere else.  With a
+ * per-block schedule, calls must end on block boundaries (as for doppler_b200_mix_blocks). */
+typedef struct doppler_b200_decim doppler_b200_decim;
+int doppler_b200_decim_create(doppler_b200_ctx* ctx, const float* taps, uint32_t ntaps, uint32_t decimation, doppler_b200_decim** out);
+void doppler_b200_decim_destroy(doppler_b200_decim* d);
+int doppler_b200_decim_reset(doppler_b200_decim* d);          /* back to the start of a stream (history zeroed) */
+uint64_t doppler_b200_decim_position(const doppler_b200_decim* d);   /* input samples consumed so far */
+int doppler_b200_mix_decimate(doppler_b200_decim* d, const void* in, size_t in_len, int intype, int outtype, float shift_hz,
+                              uint32_t samplerate, uint32_t* samplenum, void* out, size_t out_cap, size_t* out_len);
+int doppler_b200_mix_blocks_decimate(doppler_b200_decim* d, const void* in, size_t in_len, int intype, int outtype,
+                                     const float* shift_hz_per_block, size_t nblocks, size_t block_bytes, uint32_t samplerate,
+                                     uint32_t* samplenum, void* out, size_t out_cap, size_t* out_len);
+/* device buffers (16-byte aligned), asynchronous on `stream` (NULL = the context's own); one call <= 2^30 samples */
+int doppler_b200_mix_decimate_dev(doppler_b200_decim* d, const void* d_in, size_t in_len, int intype, int outtype, float shift_hz,
+                                  uint32_t samplerate, uint32_t* samplenum, void* d_out, size_t out_cap, size_t* out_len, void* stream);
+int doppler_b200_mix_blocks_decimate_dev(doppler_b200_decim* d, const void* d_in, size_t in_len, int intype, int outtype,
+                                         const float* shift_hz_per_block, size_t nblocks, size_t block_bytes, uint32_t samplerate,
+                                         uint32_t* samplenum, void* d_out, size_t out_cap, size_t* out_len, void* stream);
+
 /* ---- device-resident variants (benchmarks, GPU pipelines, time-sliced multi-GPU) ---------- */
 
 /* d_in / d_out: device pointers, 16-byte aligned, on the context's device.  `stream` is a

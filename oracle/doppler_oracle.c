@@ -467,6 +467,58 @@ double oracle_bench_blocks(const uint8_t* in, size_t nsamples, int intype, int o
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* decimating FIR fused after the mixer.  NOT in the reference (the usual  */
+/* next block after `doppler` in an SDR pipe, README.md:53); this function IS its             */
+/* specification, and the CUDA path must reproduce it bit for bit:                            */
+/*   y[k]  = the mixer's Complex<f32> result for stream sample k (dsp.rs:117-134 exactly,     */
+/*           per-block shifts as oracle_mix_blocks), y[k] = 0 for k < 0                       */
+/*   z[m]  = sum over t = 0 .. ntaps-1, in that order, of h[t] * y[m*M - t], each step one     */
+/*           fused multiply-add in f32 (fmaf), re and im separately, accumulator starting at 0 */
+/*   out   = z as raw f32 pairs, or (z * 32767.0) as i16 like main.rs:73-87                    */
+/* One output per M input samples: output m is produced by the call that supplies sample m*M. */
+/* State across calls: the last ntaps-1 mixed samples (hist, oldest first), the stream        */
+/* position *pos of the next input sample, and samplenum.  Returns bytes written or -1.      */
+long oracle_mix_decimate(const uint8_t* in, size_t len, int intype, int outtype, const float* shifts, size_t nshifts,
+                         uint32_t samplerate, uint32_t* samplenum, const float* taps, uint32_t ntaps, uint32_t M,
+                         oracle_c32* hist, uint64_t* pos, uint8_t* out)
+{
+    size_t ibps = intype == ORACLE_I16 ? 4 : 8;
+    if (len % ibps != 0 || ntaps == 0 || M == 0) return -1;
+    size_t n = len / ibps, blk = ORACLE_BUFFER_SIZE / ibps, nh = ntaps - 1;
+    if ((n + blk - 1) / blk > nshifts && n > 0) return -1;
+    /* y with its history in front: line[0 .. nh) = hist, line[nh + i] = y of this call's sample i */
+    oracle_c32* line = (oracle_c32*)malloc((nh + n + 1) * sizeof(oracle_c32));
+    oracle_c32* a = (oracle_c32*)malloc((blk + 1) * sizeof(oracle_c32));
+    memcpy(line, hist, nh * sizeof(oracle_c32));
+    for (size_t k = 0, b = 0; k < n; k += blk, b++) {
+        size_t c = n - k < blk ? n - k : blk;
+        if (intype == ORACLE_I16)
+            oracle_convert_iqi16_to_complex(in + k * ibps, c * ibps, a);
+        else
+            oracle_convert_iqf32_to_complex(in + k * ibps, c * ibps, a);
+        oracle_shift_frequency(a, c, samplenum, shifts[b], samplerate, line + nh + k);
+    }
+    size_t wr = 0;
+    uint64_t K0 = *pos;
+    for (size_t i = 0; i < n; i++) {
+        if ((K0 + i) % M != 0) continue;
+        float re = 0.0f, im = 0.0f;
+        for (uint32_t t = 0; t < ntaps; t++) {
+            const oracle_c32 y = line[nh + i - t];   /* t <= nh: never before the history */
+            re = fmaf(taps[t], y.re, re);
+            im = fmaf(taps[t], y.im, im);
+        }
+        oracle_c32 z = {re, im};
+        wr += outtype == ORACLE_I16 ? oracle_egress_i16(&z, 1, out + wr) : oracle_egress_f32(&z, 1, out + wr);
+    }
+    if (nh) memmove(hist, line + n, nh * sizeof(oracle_c32));   /* the last nh mixed samples (old history when n < nh) */
+    *pos = K0 + n;
+    free(line);
+    free(a);
+    return (long)wr;
+}
+
 /* Direct libm sincosf on a batch (checker for the product's device sincosf and its
  * host-compiled twin in tests/native). */
 void oracle_sincosf_batch(const float* theta, size_t n, float* sin_out, float* cos_out)

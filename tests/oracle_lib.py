@@ -192,6 +192,29 @@ class Oracle:
             raise RuntimeError("oracle_bench_blocks: schedule shorter than the stream")
         return float(t), out, sn.value
 
+    def mix_decimate(self, buf, intype, outtype, shifts, samplerate, taps, M, state=None):
+        """The fused mix + decimating FIR specification (oracle_mix_decimate).  `shifts`: one per 8192-byte block (a scalar
+        is repeated).  `state` = dict(samplenum, hist, pos) carried across calls (None: a fresh stream).
+        Returns (output bytes, state)."""
+        a = np.ascontiguousarray(np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf.view(np.uint8).reshape(-1))
+        h = np.ascontiguousarray(taps, dtype=np.float32)
+        n = a.size // BPS[intype]
+        nblocks = max(1, (a.size + BUFFER_SIZE - 1) // BUFFER_SIZE)
+        sh = np.ascontiguousarray(np.broadcast_to(np.asarray(shifts, dtype=np.float32), (nblocks,)) if np.ndim(shifts) == 0 else shifts, dtype=np.float32)
+        if state is None:
+            state = {"samplenum": 0, "hist": np.zeros(2 * max(h.size - 1, 1), dtype=np.float32), "pos": 0}
+        hist = np.ascontiguousarray(state["hist"], dtype=np.float32).copy()
+        sn = ctypes.c_uint32(state["samplenum"])
+        pos = ctypes.c_uint64(state["pos"])
+        out = np.empty((n // M + 2) * BPS[outtype], dtype=np.uint8)
+        self.lib.oracle_mix_decimate.restype = ctypes.c_long
+        w = self.lib.oracle_mix_decimate(_p(a), ctypes.c_size_t(a.size), intype, outtype, _p(sh), ctypes.c_size_t(sh.size),
+                                         ctypes.c_uint32(samplerate), ctypes.byref(sn), _p(h), ctypes.c_uint32(h.size), ctypes.c_uint32(M),
+                                         _p(hist), ctypes.byref(pos), _p(out))
+        if w < 0:
+            raise RuntimeError("oracle_mix_decimate: bad arguments")
+        return out[:w].copy(), {"samplenum": sn.value, "hist": hist, "pos": pos.value}
+
     def mix_blocks_threads(self, buf, intype, outtype, shifts, samplerate, samplenum=0, threads=None):
         """oracle.mix_blocks on all host cores (same bytes, same final samplenum)."""
         import os
