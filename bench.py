@@ -434,6 +434,74 @@ def run_cfg5(mixer, stream, D, peak):
     return out
 
 
+def run_f4(mixer, stream, D, peak):
+    """SURVEY 8(f) row 4, the fused downstream stage: const f32 -> i16 @ 10 Msps (the headline's input) followed by a
+    decimate-by-8 49-tap low-pass, one pass (doppler_b200_mix_decimate).  Device-resident rate, the host-buffer rate (D2H
+    shrinks by 8) and a bit-exact check of a window against the oracle's specification."""
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    import doppler_b200
+    from doppler_b200 import F32, I16, _lib
+    from tests.oracle_lib import Oracle
+    M, ntaps = 8, 49
+    t = np.arange(ntaps) - (ntaps - 1) / 2.0
+    h = np.sinc(2 * 0.05 * t) * np.hamming(ntaps)
+    taps = (h / h.sum()).astype(np.float32)
+    dec = doppler_b200.Decimator(mixer, taps, M)
+    n = 256_000_000
+    x = torch.empty(2 * n, dtype=torch.float32, device=D.dev)
+    x.uniform_(-0.7, 0.7)
+    y = torch.empty(2 * (n // M + 2), dtype=torch.int16, device=D.dev)
+    torch.cuda.synchronize()
+    times = []
+    for i in range(2 + 5):
+        dec.reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        nbytes, sn = dec.mix_dev(x.data_ptr(), 8 * n, F32, I16, SHIFT, FS, 0, y.data_ptr(), 2 * y.numel(), stream=stream.cuda_stream)
+        e1.record(stream)
+        stream.synchronize()
+        if i >= 2:
+            times.append(e0.elapsed_time(e1) * 1e-3)
+    med = D.max(statistics.median(times))
+    # parity: the first 2^20 inputs against the specification
+    w = 1 << 20
+    want, st = Oracle().mix_decimate(x[:2 * w].cpu().numpy().view(np.uint8), F32, I16, SHIFT, FS, taps, M)
+    ok = bool(np.array_equal(y[:want.size // 2].cpu().numpy().view(np.uint8), want))
+    del x, y
+    torch.cuda.empty_cache()
+    # host buffers (pinned): H2D 8 B/sample, D2H 4/8 B/sample
+    lib = _lib.load()
+    ne = 160_000_000
+    hin, hout = lib.doppler_b200_host_alloc(8 * ne), lib.doppler_b200_host_alloc(4 * (ne // M + 2))
+    a_in = np.ctypeslib.as_array(ctypes.cast(hin, ctypes.POINTER(ctypes.c_float)), shape=(2 * ne,))
+    a_in[:] = np.random.default_rng(4 + D.rank).uniform(-0.7, 0.7, 2 * ne).astype(np.float32)
+    tt = []
+    for i in range(1 + 3):
+        dec.reset()
+        snc, got = ctypes.c_uint32(0), ctypes.c_size_t(0)
+        D.barrier()
+        t0 = time.perf_counter()
+        rc = lib.doppler_b200_mix_decimate(dec._d, hin, 8 * ne, F32, I16, ctypes.c_float(SHIFT), FS, ctypes.byref(snc), hout, 4 * (ne // M + 2), ctypes.byref(got))
+        dt = D.max(time.perf_counter() - t0)
+        if rc != 0:
+            raise RuntimeError(f"doppler_b200_mix_decimate failed rc={rc}")
+        if i >= 1:
+            tt.append(dt)
+    lib.doppler_b200_host_free(hin)
+    lib.doppler_b200_host_free(hout)
+    dec.close()
+    bps = 8 + 4.0 / M
+    return {"workload": f"const f32 @ 10 Msps --shift 100000 -> mixer -> {ntaps}-tap low-pass, decimate by {M} -> i16 (one pass)",
+            "samples_per_gpu": n, "ms_per_call": med * 1e3, "msps_in": D.world * n / med / 1e6, "bytes_per_input_sample": bps,
+            "frac": n * bps / med / 1e9 / peak, "parity_ok": D.all_true(ok), "parity_samples_checked": w,
+            "e2e_msps_in": D.world * ne / statistics.median(tt) / 1e6, "e2e_d2h_bytes": 4 * (ne // M),
+            "note": "not in the reference (SURVEY 8f row 4); specification = oracle_mix_decimate; first correct version, not tuned to the roofline"}
+
+
 def run_cfg1_cli(oracle_threads):
     """cfg1: `doppler const -s 256000 -i i16 --shift -15000` over 1 s of i16 IQ through the CLI (stdin -> stdout), bytes
     compared with the oracle's restatement of the reference's const driver.  Wall clock of the whole process (CUDA
@@ -654,6 +722,7 @@ def main():
         configs["cfg3"] = run_cfg3(mixer, tstream, D, peak, oracle_threads)
         configs["cfg4"] = run_cfg4(mixer, tstream, D, peak, oracle_threads)
         configs["cfg5"] = run_cfg5(mixer, tstream, D, peak)
+        configs["f4_mix_decimate"] = run_f4(mixer, tstream, D, peak)
         if rank == 0:
             configs["cfg1"] = run_cfg1_cli(oracle_threads)
         configs["gpu_seconds"] = time.time() - t_c

@@ -631,7 +631,7 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
             const bool one_cta = done != nullptr && groups <= (uint32_t)dmix::kSmallThreads * kSmallV;
             const bool wide = one_cta || groups > (uint32_t)ctx->sm_count * 8u * dmix::kSmallThreads;
             const uint32_t per_cta = (uint32_t)dmix::kSmallThreads * (wide ? kSmallV : 1);
-            const uint32_t ctas = one_cta ? 1u : std::min<uint32_t>((groups + per_cta - 1) / per_cta, (uint32_t)ctx->sm_count * 32u);
+            const uint32_t ctas = one_cta ? 1u : std::min<uint32_t>((groups + per_cta - 1) / per_cta, (uint32_t)ctx->sm_count * 8u);   // one resident wave
             small_kernel_for(intype, outtype, wide)<<<ctas, dmix::kSmallThreads, 0, s>>>(a, done ? *done : dmix::SmallDone{nullptr, nullptr, 0});
         } else {
             shape.kern<<<grid, shape.warps * 32, smem, s>>>(a);

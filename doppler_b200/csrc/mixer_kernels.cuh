@@ -796,9 +796,17 @@ struct TileIter {
 
 #if defined(__CUDACC__)
 // Device tile source: every member is executed by ALL lanes of the warp (warp-convergent); results are warp-uniform.
+// Units are claimed in CHUNKS of consecutive units whose size follows the work that is left (guided self-scheduling):
+// up to kMaxClaim while the launch is young -- consecutive units mostly share a segment, so the segment lookup (two to
+// three dependent global loads) and the atomic are paid once per chunk -- down to single units near the end, where
+// balance between the pipelines matters.  The claim for the NEXT chunk is issued when a chunk starts, so its latency
+// hides behind the chunk's tiles.
+constexpr uint32_t kMaxClaim = 8;
 template <typename C>
 struct TileSrc {
-    uint32_t nunits, pending;          // pending (lane 0): the unit claimed while the previous one was being set up
+    uint32_t nunits, npipes;
+    uint32_t pending, pending_cnt;     // pending (lane 0): first unit of the chunk claimed ahead; pending_cnt: its size
+    uint32_t u_cur, u_end;             // units left in the current chunk
     uint32_t seg, seg_unit_end;        // current segment
     UnitPos up;
     uint32_t t_next, batch;            // next tile of the unit to hand out; tile index held by lane 0
@@ -807,10 +815,20 @@ struct TileSrc {
     bool first;
     uint32_t dk0, dns, dskip, dinfo;   // lane-held: tile (batch + lane) of the unit
 
-    __device__ __forceinline__ void init(const MixArgs& a, uint32_t lane)
+    __device__ __forceinline__ uint32_t claim_size(uint32_t claimed) const
+    {
+        const uint32_t left = claimed < nunits ? nunits - claimed : 0u;
+        const uint32_t c = left / (4u * npipes);
+        return c < 1u ? 1u : (c > kMaxClaim ? kMaxClaim : c);
+    }
+
+    __device__ __forceinline__ void init(const MixArgs& a, uint32_t lane, uint32_t npipes_)
     {
         nunits = a.nunits;
-        pending = lane == 0 ? atomicAdd(a.unit_counter, 1u) : 0u;
+        npipes = npipes_;
+        pending_cnt = claim_size(0);
+        pending = lane == 0 ? atomicAdd(a.unit_counter, pending_cnt) : 0u;
+        u_cur = u_end = 0;
         seg = 0;
         seg_unit_end = get_seg(a, 0).unit_end;
         up.ntiles = up.c = up.j0 = 0;
@@ -855,9 +873,15 @@ struct TileSrc {
                 first = false;
                 return true;
             }
-            const uint32_t u = __shfl_sync(0xffffffffu, pending, 0);
-            if (u >= nunits) return false;
-            if (lane == 0) pending = atomicAdd(a.unit_counter, 1u);   // for the unit after this one: its latency hides behind this unit
+            if (u_cur >= u_end) {   // chunk exhausted: take the one claimed earlier, claim the one after
+                const uint32_t base = __shfl_sync(0xffffffffu, pending, 0);
+                if (base >= nunits) return false;
+                u_cur = base;
+                u_end = base + pending_cnt < nunits ? base + pending_cnt : nunits;
+                pending_cnt = claim_size(u_end);
+                if (lane == 0) pending = atomicAdd(a.unit_counter, pending_cnt);
+            }
+            const uint32_t u = u_cur++;
             if (u >= seg_unit_end) {
                 // jump through the coarse unit -> segment index, then walk the last few segments
                 if (a.nsegs > (uint32_t)kInlineSegs) {
@@ -916,7 +940,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
     // the warp expands its work units into tiles together (TileSrc); lane 0 issues the tile's bulk load and parks the
     // descriptor in shared memory for the compute stage
     TileSrc<C> src;
-    src.init(a, lane);
+    src.init(a, lane, npipes);
     auto issue_next = [&](uint32_t s) {   // all lanes (warp-convergent)
         TileDesc d;
         const bool more = src.fetch(a, lane, d);
@@ -1180,13 +1204,17 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
     const uint32_t ngroups = a.nsamples / G;
     uint32_t pi = 0;
     DevPiece p = get_piece(a, 0);
-    for (uint32_t base = blockIdx.x * kStep; base < ngroups; base += gridDim.x * kStep) {
+    // every CTA takes an equal, contiguous share of the groups (a grid-stride loop over fixed steps leaves whole steps
+    // unevenly spread: 2.06 steps per CTA means a third of the CTAs run 3 while the rest wait)
+    const uint32_t g_begin = (uint32_t)((uint64_t)ngroups * blockIdx.x / gridDim.x);
+    const uint32_t g_end = (uint32_t)((uint64_t)ngroups * (blockIdx.x + 1) / gridDim.x);
+    for (uint32_t base = g_begin; base < g_end; base += kStep) {
         uint32_t w[V][4];
 #pragma unroll
         for (int v = 0; v < V; v++) {
             const uint32_t g = base + v * kSmallThreads + threadIdx.x;
             w[v][0] = w[v][1] = w[v][2] = w[v][3] = 0;
-            if (g < ngroups) {
+            if (g < g_end) {
                 if constexpr (IN == I16 && G == 2) {
                     const uint2 x = __ldcs(reinterpret_cast<const uint2*>(a.in) + g);
                     w[v][0] = x.x, w[v][1] = x.y;
@@ -1199,7 +1227,7 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
 #pragma unroll
         for (int v = 0; v < V; v++) {
             const uint32_t g = base + v * kSmallThreads + threadIdx.x;
-            if (g >= ngroups) break;
+            if (g >= g_end) break;
             const uint32_t k0 = g * G;
             float2 smp[G], res[G];
             if constexpr (IN == I16) {

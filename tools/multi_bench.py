@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""tools/multi_bench.py -- the time-sliced multi-GPU entry points from ONE process (include/doppler_b200.h:
+doppler_b200_multi_*), on every GPU of the box.
+
+(a) BASELINE configs[3] whole: track f32->f32 @ 200 Msps, 60 s overpass = 12 G samples, one contiguous time slice per GPU,
+    device-resident, through doppler_b200_mix_blocks_multi_dev; wall clock around call + synchronize, parity windows vs the oracle
+    at every slice boundary;
+(b) the headline workload (const f32->i16 @ 10 Msps) through doppler_b200_mix_multi with pinned HOST buffers: H2D + kernels +
+    D2H on all GPUs at once from one call.
+One JSON line."""
+import ctypes
+import json
+import os
+import statistics
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import doppler_b200  # noqa: E402
+from doppler_b200 import F32, I16, _lib, dsp  # noqa: E402
+from tests.oracle_lib import Oracle  # noqa: E402
+from tools import workloads as W  # noqa: E402
+
+
+def main():
+    ndev = torch.cuda.device_count()
+    m = doppler_b200.MultiMixer(list(range(ndev)))
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    out = {"n_gpus": ndev, "process": "one process, one context + one host thread per GPU (doppler_b200_multi_create)"}
+
+    # (a) cfg4 whole job, device resident
+    c = W.CFG4
+    fs, total, bs = c["fs"], c["secs"] * c["fs"], 1024
+    if ndev < 8:
+        total = total * ndev // 8 // bs * bs            # fewer GPUs: the same 1.5 G samples per GPU
+    shifts = W.cfg_schedule(c)
+    begins, seeds = dsp.slice_seeds(0, shifts, bs, fs, total, ndev)
+    xs, ys = [], []
+    for d in range(ndev):
+        n = begins[d + 1] - begins[d]
+        with torch.cuda.device(d):
+            x = torch.empty(n * 8, dtype=torch.uint8, device=f"cuda:{d}")
+            W.fill_device(x, F32)
+            xs.append(x)
+            ys.append(torch.empty(n * 8, dtype=torch.uint8, device=f"cuda:{d}"))
+    pin, lin = [t.data_ptr() for t in xs], [t.numel() for t in xs]
+    pout, lout = [t.data_ptr() for t in ys], [t.numel() for t in ys]
+
+    def call():
+        sn = m.mix_blocks_dev(pin, lin, F32, F32, shifts, fs, 0, pout, lout)
+        m.synchronize()
+        return sn
+
+    sn = call()
+    call()
+    times = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        call()
+        times.append(time.perf_counter() - t0)
+    ok = sn == seeds[-1]
+    oracle = Oracle()
+    threads = len(os.sched_getaffinity(0))
+    half = 1 << 22
+    checked = 0
+    for d in range(ndev):
+        n = begins[d + 1] - begins[d]
+        wins = [(0, half), ((n - half) // bs * bs, n)]
+        o, cnt, _ = W.check_windows(oracle, xs[d], ys[d], F32, F32, shifts, fs, begins[d], wins, threads)
+        ok, checked = ok and o, checked + cnt
+    t = statistics.median(times)
+    out["cfg4_device_resident"] = {"samples_total": total, "ms_whole_job": t * 1e3, "msps": total / t / 1e6, "frac_per_gpu": total * 16 / ndev / t / 1e9 / peak,
+                                   "timing": "wall clock around doppler_b200_mix_blocks_multi_dev + doppler_b200_multi_synchronize, median of 5",
+                                   "parity_ok": bool(ok), "parity_samples_checked": checked,
+                                   "parity_windows": "2^22 samples on each side of every slice boundary, bit-exact vs the oracle; final samplenum == analytic"}
+    del xs, ys
+    for d in range(ndev):
+        with torch.cuda.device(d):
+            torch.cuda.empty_cache()
+
+    # (b) headline workload through host buffers, all GPUs from one call
+    lib = _lib.load()
+    ne = 160_000_000 * max(1, min(ndev, 4))
+    hin, hout = lib.doppler_b200_host_alloc(8 * ne), lib.doppler_b200_host_alloc(4 * ne)
+    a_in = np.ctypeslib.as_array(ctypes.cast(hin, ctypes.POINTER(ctypes.c_float)), shape=(2 * ne,))
+    a_out = np.ctypeslib.as_array(ctypes.cast(hout, ctypes.POINTER(ctypes.c_uint8)), shape=(4 * ne,))
+    a_in[:] = np.random.default_rng(3).uniform(-0.7, 0.7, 2 * ne).astype(np.float32)
+    tt = []
+    for i in range(2 + 4):
+        snc, got = ctypes.c_uint32(0), ctypes.c_size_t(0)
+        t0 = time.perf_counter()
+        rc = lib.doppler_b200_mix_multi(m._m, hin, 8 * ne, F32, I16, ctypes.c_float(100000.0), 10_000_000, ctypes.byref(snc), hout, 4 * ne, ctypes.byref(got))
+        dt = time.perf_counter() - t0
+        assert rc == 0 and got.value == 4 * ne
+        if i >= 2:
+            tt.append(dt)
+    w = 1 << 20
+    want, _ = oracle.mix(a_in[:2 * w].view(np.uint8), F32, I16, 100000.0, 10_000_000)
+    tail0 = (ne - w) // 1024 * 1024
+    want_t, sn_t = oracle.mix(a_in[2 * tail0:].view(np.uint8), F32, I16, 100000.0, 10_000_000, samplenum=dsp.samplenum_advance(0, 100000.0, 10_000_000, tail0))
+    okb = bool(np.array_equal(a_out[:4 * w], want) and np.array_equal(a_out[4 * tail0:], want_t) and sn_t == snc.value)
+    out["headline_host_buffers"] = {"samples_per_call": ne, "msps": ne / statistics.median(tt) / 1e6, "parity_ok": okb,
+                                    "api": "doppler_b200_mix_multi, pinned host buffers (doppler_b200_host_alloc)"}
+    lib.doppler_b200_host_free(hin)
+    lib.doppler_b200_host_free(hout)
+    m.close()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
