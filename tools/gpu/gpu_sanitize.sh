@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer over the kernels' paths (small inputs): memcheck, racecheck (shared-memory hazards), synccheck
-OUT=gpurun_out/${1:-r01v}
+OUT=gpurun_out/${1:-r02san}
 mkdir -p $OUT
 cat > /tmp/san_case.py <<'PY'
 import sys
@@ -28,6 +28,44 @@ for it, ot in [(I16, I16), (I16, F32), (F32, I16), (F32, F32)]:
         ok = sn == sn_ref and np.array_equal(got, want)
         bad += not ok
         print(it, ot, shift, n, "ok" if ok else "MISMATCH")
+# round 2: the bulk-async kernels on the same short inputs (small kernel and zero-copy path off), the plateau path of direct
+# evaluation (samplenum above 2^24), the zero-copy per-block host path, the multi-context group, the fused decimator
+m.tune(small_max_samples=0, tiny_host_bytes=0)
+for it, ot in [(I16, I16), (F32, I16)]:
+    for shift, fs, n, sn0 in [(-15000.0, 256000, 70_001, 0), (1.0, 2_000_000_000, 300_001, 2**26 + 5), (7321.7, 1_024_000, 130_001, 0)]:
+        buf = (rng.integers(-32768, 32768, 2 * n, dtype=np.int32).astype(np.int16) if it == I16 else rng.uniform(-0.7, 0.7, 2 * n).astype(np.float32)).view(np.uint8)
+        got, sn = m.mix(buf, it, ot, shift, fs, samplenum=sn0)
+        want, sn_ref = o.mix(buf, it, ot, shift, fs, samplenum=sn0)
+        ok = sn == sn_ref and np.array_equal(got, want)
+        bad += not ok
+        print("bulk", it, ot, shift, n, "ok" if ok else "MISMATCH")
+m.tune(small_max_samples=4 << 20, tiny_host_bytes=128 << 10)
+for n in (1, 2048, 2049, 30_001):
+    buf = rng.integers(-32768, 32768, 2 * n, dtype=np.int32).astype(np.int16).view(np.uint8)
+    got, sn = m.mix(buf, I16, I16, 5000.0, 1_024_000)
+    want, sn_ref = o.mix(buf, I16, I16, 5000.0, 1_024_000)
+    ok = sn == sn_ref and np.array_equal(got, want)
+    bad += not ok
+    print("tiny", n, "ok" if ok else "MISMATCH")
+g = doppler_b200.MultiMixer([0, 0])
+buf = rng.uniform(-0.7, 0.7, 2 * 200_003).astype(np.float32).view(np.uint8)
+got, sn = g.mix(buf, F32, I16, 100000.0, 10_000_000)
+want, sn_ref = o.mix(buf, F32, I16, 100000.0, 10_000_000)
+ok = sn == sn_ref and np.array_equal(got, want)
+bad += not ok
+print("multi", "ok" if ok else "MISMATCH")
+g.close()
+taps = (np.hamming(33) / np.hamming(33).sum()).astype(np.float32)
+d = doppler_b200.Decimator(m, taps, 8)
+st, sn = None, 0
+for n in (5, 70_001, 200_003):
+    buf = rng.integers(-32768, 32768, 2 * n, dtype=np.int32).astype(np.int16).view(np.uint8)
+    got, sn = d.mix(buf, I16, I16, 7321.7, 1_024_000, samplenum=sn)
+    want, st = o.mix_decimate(buf, I16, I16, 7321.7, 1_024_000, taps, 8, st)
+    ok = sn == st["samplenum"] and np.array_equal(got, want)
+    bad += not ok
+    print("decimate", n, "ok" if ok else "MISMATCH")
+d.close()
 m.close()
 sys.exit(1 if bad else 0)
 PY
