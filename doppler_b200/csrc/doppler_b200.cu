@@ -728,9 +728,10 @@ public:
             memcpy(dst, src, bytes);
             return;
         }
-        while (workers_.size() + 1 < want) {
+        while (workers_.size() + 1 < want) {   // (no job is in flight here: copy() returns only when all workers are done)
             const size_t id = workers_.size();
-            workers_.emplace_back([this, id] { run(id); });
+            const uint64_t gen = generation_;   // a new worker must not mistake an earlier job for a fresh one
+            workers_.emplace_back([this, id, gen] { run(id, gen); });
         }
         const size_t parts = workers_.size() + 1;
         const size_t part = (bytes / parts + 4095) & ~(size_t)4095;
@@ -751,9 +752,8 @@ public:
 
 private:
     static constexpr int kMaxThreads = 8;
-    void run(size_t id)
+    void run(size_t id, uint64_t seen)
     {
-        uint64_t seen = 0;
         for (;;) {
             char* dst;
             const char* src;
