@@ -132,6 +132,7 @@ struct doppler_b200_ctx {
     std::string err;
     uint64_t launches = 0;
     uint32_t small_max = kSmallMaxSamples;
+    bool seg_alt = false;               // doppler_b200_tune: use StreamShape::seg_alt
     size_t tiny_host_bytes = kTinyHostBytes;
     // zero-copy per-block host path: completion flag in mapped host memory + CTA counter on the device
     uint32_t* done_flag = nullptr;      // host (pinned)
@@ -181,11 +182,12 @@ struct KernShape {
     uint32_t (*table_bytes)(uint32_t period);
     uint32_t smem_tab_entries;   // longest period whose table this kernel stages in shared memory
     uint32_t scratch_smem;       // per-CTA plateau scratch (direct-evaluation shape of the lean kernel), part of fixed_smem
+    int pipes;                   // pipelines per CTA (= warps, or warps / Q for the Q-warp pipelines)
 };
 // Per (intype, outtype): the lean loop for a launch that is one GRID segment (const mode), and the
 // segmented loop (GRID + COLUMN segments) with its own, larger tile.
 struct StreamShape {
-    KernShape grid, seg;
+    KernShape grid, seg, seg_alt;   // seg_alt: the other form of the segmented kernel (A/B through doppler_b200_tune)
     KernShape direct;   // the lean loop with a larger tile, for launches whose samples are mostly in table-less pieces:
                         // direct evaluation is issue-bound, so the per-tile pipeline overhead is what there is to save
 };
@@ -212,12 +214,23 @@ KernShape make_shape()
     else
         kern = dmix::mix_grid_kernel<IN, OUT, WARPS, S, U>;
     return KernShape{kern, WARPS, (uint32_t)C::kTileSamples, (uint32_t)C::kRow, (uint32_t)C::kGran, fixed, &C::table_bytes,
-                     smem_tab_capacity(fixed, (uint32_t)C::kRow), scratch};
+                     smem_tab_capacity(fixed, (uint32_t)C::kRow), scratch, WARPS};
+}
+
+// Q-warp pipelines (mix_pipe_kernel)
+template <int IN, int OUT, int WARPS, int S, int U, int Q>
+KernShape make_pipe_shape()
+{
+    using P = dmix::PipeCfg<IN, OUT, WARPS, S, U, Q>;
+    return KernShape{dmix::mix_pipe_kernel<IN, OUT, WARPS, S, U, Q>, WARPS, (uint32_t)P::kTileSamples, (uint32_t)P::kRow, (uint32_t)P::kGran,
+                     (uint32_t)P::kFixedSmem, &P::table_bytes, smem_tab_capacity((uint32_t)P::kFixedSmem, (uint32_t)P::kRow), 0u, P::kPipes};
 }
 
 // (WARPS, S, U) of the segmented kernel per type pair; the host walk of the work decomposition
-// (doppler_b200_plan_tiles_trace) instantiates the same configurations.
-using SegI16I16 = dmix::StreamCfg<0, 0, SEG_I16I16>;
+// (doppler_b200_plan_tiles_trace) instantiates the same configurations.  i16 -> i16 (issue-bound at 8 bytes per sample)
+// runs 4-warp pipelines; `SegI16I16W` is the per-warp form of round 1, kept selectable (doppler_b200_tune) for A/B runs.
+using SegI16I16 = dmix::PipeCfg<0, 0, SEG_I16I16, 4>;
+using SegI16I16W = dmix::StreamCfg<0, 0, SEG_I16I16>;
 using SegI16F32 = dmix::StreamCfg<0, 1, SEG_I16F32>;
 using SegF32I16 = dmix::StreamCfg<1, 0, SEG_F32I16>;
 using SegF32F32 = dmix::StreamCfg<1, 1, SEG_F32F32>;
@@ -229,10 +242,14 @@ const StreamShape& shape_for(int in, int out)
     // isolated launches prefer (24,2,2) for f32->i16, r01_tune_stream_smemtab_fmul2.jsonl).
     // direct shapes: profiles/r01_tune_direct_linear.jsonl
     static const StreamShape shapes[2][2] = {
-        {{make_shape<0, 0, 20, 2, 2, false>(), make_shape<0, 0, SEG_I16I16, true>(), make_shape<0, 0, 12, 2, 6, false, true>()},
-         {make_shape<0, 1, 20, 3, 2, false>(), make_shape<0, 1, SEG_I16F32, true>(), make_shape<0, 1, 16, 2, 4, false, true>()}},
-        {{make_shape<1, 0, 16, 2, 3, false>(), make_shape<1, 0, SEG_F32I16, true>(), make_shape<1, 0, 16, 2, 6, false, true>()},
-         {make_shape<1, 1, 16, 2, 2, false>(), make_shape<1, 1, SEG_F32F32, true>(), make_shape<1, 1, 16, 2, 2, false, true>()}},
+        {{make_shape<0, 0, 20, 2, 2, false>(), make_pipe_shape<0, 0, SEG_I16I16, 4>(), make_shape<0, 0, SEG_I16I16, true>(),
+          make_shape<0, 0, 12, 2, 6, false, true>()},
+         {make_shape<0, 1, 20, 3, 2, false>(), make_shape<0, 1, SEG_I16F32, true>(), make_shape<0, 1, SEG_I16F32, true>(),
+          make_shape<0, 1, 16, 2, 4, false, true>()}},
+        {{make_shape<1, 0, 16, 2, 3, false>(), make_shape<1, 0, SEG_F32I16, true>(), make_shape<1, 0, SEG_F32I16, true>(),
+          make_shape<1, 0, 16, 2, 6, false, true>()},
+         {make_shape<1, 1, 16, 2, 2, false>(), make_shape<1, 1, SEG_F32F32, true>(), make_shape<1, 1, SEG_F32F32, true>(),
+          make_shape<1, 1, 16, 2, 2, false, true>()}},
     };
     return shapes[in][out];
 }
@@ -500,9 +517,10 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
     ctx->planner.plan(runs, 0, &sn_after, &pieces);
 
     const StreamShape& shapes = shape_for(intype, outtype);
+    const KernShape& seg_shape = ctx->seg_alt ? shapes.seg_alt : shapes.seg;
     const size_t ibps = bytes_per_sample(intype), obps = bytes_per_sample(outtype);
     // launches are cut at a common multiple of both kernels' tiles so that every launch but the last has no ragged tail
-    const uint64_t lcm_tile = std::lcm<uint64_t>(std::lcm<uint64_t>(shapes.grid.tile_samples, shapes.seg.tile_samples), shapes.direct.tile_samples);
+    const uint64_t lcm_tile = std::lcm<uint64_t>(std::lcm<uint64_t>(shapes.grid.tile_samples, std::lcm<uint64_t>(shapes.seg.tile_samples, shapes.seg_alt.tile_samples)), shapes.direct.tile_samples);
     const uint64_t launch_max = kLaunchMaxSamples / lcm_tile * lcm_tile;
 
     // table builds are ordered before this launch: by stream order when they were enqueued on `s` itself, through the event otherwise
@@ -515,7 +533,8 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         std::vector<uint64_t> dev_len;
         // DevPiece::step_u is baked from the row width, which depends on the type pair only (kRow = 32 * G): one value serves all three shapes
         static_assert(SegI16I16::kRow == 128 && SegI16F32::kRow == 64 && SegF32I16::kRow == 64 && SegF32F32::kRow == 64, "row width per type pair");
-        if (shapes.grid.row_samples != shapes.seg.row_samples || shapes.grid.row_samples != shapes.direct.row_samples)
+        if (shapes.grid.row_samples != shapes.seg.row_samples || shapes.grid.row_samples != shapes.direct.row_samples ||
+            shapes.grid.row_samples != shapes.seg_alt.row_samples)
             return fail(ctx, DOPPLER_B200_EINVAL, "kernel shapes of one type pair disagree on the row width");
         clip_pieces(pieces, l0, l1, shapes.grid.row_samples, &dev, &src);
         for (size_t i = 0; i < dev.size(); i++) {
@@ -541,13 +560,12 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         std::vector<DevSeg> segs;
         uint32_t tail_begin = nsamp;
         if (!small)
-            tail_begin = build_segments(dev, nsamp, shapes.seg.tile_samples, shapes.seg.gran,
-                                        (uint32_t)ctx->sm_count * (uint32_t)shapes.seg.warps, &segs);
+            tail_begin = build_segments(dev, nsamp, seg_shape.tile_samples, seg_shape.gran, (uint32_t)ctx->sm_count * (uint32_t)seg_shape.pipes, &segs);
         // no COLUMN segment: the whole launch is one GRID segment and takes the lean loop
         const bool grid_only = small || (segs.size() <= 1 && (segs.empty() || segs[0].rows == 0));
         uint64_t tableless = 0;
         for (size_t i = 0; i < dev.size(); i++) tableless += dev[i].tab == dmix::kNoTab ? dev_len[i] : 0;
-        const KernShape& shape = !grid_only ? shapes.seg : 2 * tableless > nsamp ? shapes.direct : shapes.grid;
+        const KernShape& shape = !grid_only ? seg_shape : 2 * tableless > nsamp ? shapes.direct : shapes.grid;
         // one table per launch is staged in shared memory: the eligible piece covering most samples
         uint32_t smem_piece = dmix::kNoPiece;
         uint64_t smem_piece_len = 0;
@@ -571,7 +589,7 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         a.plateau_scratch = shape.scratch_smem != 0;
         // persistent: one CTA per SM, every warp an independent pipeline over interleaved work units
         if (grid_only) a.nunits = nsamp / shape.tile_samples;   // whole tiles; the lean loop mixes the ragged end itself
-        const uint32_t want = (a.nunits + shape.warps - 1) / shape.warps;
+        const uint32_t want = (a.nunits + shape.pipes - 1) / shape.pipes;
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->sm_count, want));
         const size_t smem = shape.fixed_smem + (smem_piece != dmix::kNoPiece ? shape.table_bytes(dev[smem_piece].period) : 0);
 
@@ -1046,7 +1064,7 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     for (int i = 0; i < 2 && e2 == cudaSuccess; i++)
         for (int o = 0; o < 2 && e2 == cudaSuccess; o++) {
             const StreamShape& sh = shape_for(i, o);
-            for (const KernShape* k : {&sh.grid, &sh.seg, &sh.direct})
+            for (const KernShape* k : {&sh.grid, &sh.seg, &sh.seg_alt, &sh.direct})
                 if (e2 == cudaSuccess)
                     e2 = cudaFuncSetAttribute(k->kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)(k->fixed_smem + k->table_bytes(k->smem_tab_entries)));
@@ -1144,6 +1162,9 @@ int doppler_b200_tune(doppler_b200_ctx* ctx, int knob, uint64_t value)
         CUDA_TRY(ctx, cudaSetDevice(ctx->device));
         abandon_slots(ctx);
         ctx->tiny_host_bytes = (size_t)value;
+        return DOPPLER_B200_OK;
+    case DOPPLER_B200_TUNE_SEG_VARIANT:
+        ctx->seg_alt = value != 0;
         return DOPPLER_B200_OK;
     default:
         return fail(ctx, DOPPLER_B200_EINVAL, "unknown tuning knob %d", knob);

@@ -667,11 +667,11 @@ __device__ __forceinline__ void eval_window(float2* win, float r, uint32_t perio
 }
 
 // COLUMN: one row tile against the parked window; sh = the row's phase shift s_j.
-template <typename C, int IN, int OUT>
+template <typename C, int IN, int OUT, int PL = C::kWinPlane>
 __device__ __forceinline__ void stream_tile_column(const uint32_t (&raw)[C::U][4], unsigned char* out_s, const float2* win,
                                                    uint32_t sh, uint32_t lane)
 {
-    constexpr int G = C::G, U = C::U, PL = C::kWinPlane;
+    constexpr int G = C::G, U = C::U;
     constexpr int LOGG = G == 4 ? 2 : 1;
 #pragma unroll
     for (int u = 0; u < U; u++) {
@@ -1039,6 +1039,219 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
     // sub-granule end of the buffer (fewer than kGran samples): pipeline 0 mixes it straight from
     // global memory, sample by sample
     if (a.tail_begin < a.nsamples && pipe == 0) {
+        pi = find_piece(a, 0, a.tail_begin);
+        p = get_piece(a, pi);
+        for (uint32_t k = a.tail_begin + lane; k < a.nsamples; k += 32) {
+            if (k >= p.k_end) {
+                pi = find_piece(a, pi, k);
+                p = get_piece(a, pi);
+            }
+            const float2 ph = phasor(p.r, piece_samplenum(p, k - p.k_begin));
+            store_sample<OUT>(a.out, k, cmul_unfused(load_sample<IN>(a.in, k), ph));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pipelines of Q warps (round 2, i16 -> i16).  At 8 bytes per sample the segmented kernel is bound by instruction issue,
+// and a third of what it issues is per-TILE work: barrier wait and tile loads, unit expansion and bulk-load issue, fence and
+// bulk-store issue -- ~150 instructions per 512-sample tile (ncu source view, profiles/r02_ncu_cfg3_before.txt).  Here Q
+// warps share one pipeline: one bulk load brings a tile Q times as large, every warp multiplies its own sub-tile exactly
+// as before (same per-warp code), one bulk store takes the result; the expansion and both issues are paid once per Q
+// sub-tiles, by the pipeline's first warp.  Shared memory per SM is unchanged (Q sub-tiles per stage instead of Q stages
+// of one); the warps of a pipeline meet at a named barrier (bar.sync) where a single warp used __syncwarp.
+template <int IN, int OUT, int WARPS_, int S_, int U_, int Q_>
+struct PipeCfg {
+    using W = StreamCfg<IN, OUT, WARPS_, S_, U_>;   // the per-warp view the compute code is written against
+    static constexpr int WARPS = WARPS_, S = S_, U = U_, Q = Q_;
+    static constexpr int G = W::G, kGran = W::kGran, kRow = W::kRow;
+    static constexpr int kPipes = WARPS / Q;                          // pipelines per CTA
+    static constexpr int kTileSamples = Q * W::kTileSamples;          // what the work decomposition (TileSrc, host walk) sees
+    static constexpr int kTileIn = Q * W::kTileIn, kTileOut = Q * W::kTileOut;
+    static constexpr int kRing = S * (kTileIn + kTileOut);            // per pipeline
+    static constexpr int kBarBytes = ((kPipes * S * 8 + 127) / 128) * 128;
+    static constexpr int kDescBytes = S * (int)sizeof(TileDesc);      // per pipeline
+    static constexpr int kWinIters = (kTileSamples + kWinLead + 1 + Q * 32 - 1) / (Q * 32);   // per thread of the pipeline
+    static constexpr int kWinPlane = ((Q * 32 * kWinIters / G + 15) / 16) * 16 + 16 / G;
+    static constexpr int kWinBytes = G * kWinPlane * 8;               // per pipeline
+    static constexpr int kFixedSmem = kBarBytes + kPipes * (kRing + kDescBytes + kWinBytes);
+    static_assert(WARPS % Q == 0 && kPipes <= 15, "one named barrier per pipeline");
+    static_assert(G * kWinPlane >= Q * W::kPlateauEntries, "the COLUMN window doubles as the warps' plateau scratch");
+    __host__ __device__ static constexpr uint32_t plane_len(uint32_t period) { return W::plane_len(period); }
+    __host__ __device__ static constexpr uint32_t table_bytes(uint32_t period) { return W::table_bytes(period); }
+};
+
+// the COLUMN window of a Q-warp pipeline, evaluated by all of its threads (tq = thread index within the pipeline)
+template <typename P>
+__device__ __forceinline__ void eval_window_pipe(float2* win, float r, uint32_t period, uint32_t phase0, uint32_t tq)
+{
+    constexpr int G = P::G, NW = P::kWinIters, PL = P::kWinPlane, NT = P::Q * 32;
+    const uint32_t f0 = phase0 >= (uint32_t)kWinLead ? phase0 - kWinLead : phase0 + period - kWinLead;
+    const bool mono = f0 + (uint32_t)(NT * NW) <= period;   // no period wrap inside the window
+    db_window_t dt;
+    const int range = mono ? classify_tile(r, f0 + 1u, f0 + (uint32_t)(NT * NW), dt) : (int)kRangeGeneric;
+    float2* dst = win + (tq % G) * PL + tq / G;   // entry e = tq + NT*it -> plane e % G, slot e / G
+    const uint32_t nl = f0 + 1u + tq;
+    if (range == kRangeLarge) {
+#pragma unroll 3
+        for (int it = 0; it < NW; it++) dst[it * (NT / G)] = phasor_fast<kRangeLarge>(theta_of(r, nl + (uint32_t)(NT * it)), dt);
+    } else if (range == kRangeMedium) {
+#pragma unroll 3
+        for (int it = 0; it < NW; it++) dst[it * (NT / G)] = phasor_fast<kRangeMedium>(theta_of(r, nl + (uint32_t)(NT * it)), dt);
+    } else if (range == kRangeSmall) {
+#pragma unroll 3
+        for (int it = 0; it < NW; it++) dst[it * (NT / G)] = phasor_fast<kRangeSmall>(theta_of(r, nl + (uint32_t)(NT * it)), dt);
+    } else if (range == kRangeTiny) {
+#pragma unroll 3
+        for (int it = 0; it < NW; it++) dst[it * (NT / G)] = phasor_fast<kRangeTiny>(theta_of(r, nl + (uint32_t)(NT * it)), dt);
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < NW; it++) {
+            uint32_t f = f0 + tq + (uint32_t)(NT * it);
+            if (f >= period) f -= period;
+            if (f >= period) f %= period;
+            dst[it * (NT / G)] = phasor(r, f + 1u);
+        }
+    }
+}
+
+template <int IN, int OUT, int WARPS, int S, int U, int Q>
+__global__ void __launch_bounds__(WARPS * 32, 1) mix_pipe_kernel(const __grid_constant__ MixArgs a)
+{
+    using P = PipeCfg<IN, OUT, WARPS, S, U, Q>;
+    using W = typename P::W;
+    constexpr int G = W::G;
+    constexpr uint32_t kInBps = IN == I16 ? 4 : 8, kOutBps = OUT == I16 ? 4 : 8;
+    constexpr uint32_t kSub = W::kTileSamples;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    unsigned char* rings = smem + P::kBarBytes;
+    unsigned char* descs = rings + P::kPipes * P::kRing;
+    unsigned char* wins = descs + P::kPipes * P::kDescBytes;
+    float2* tab_s = reinterpret_cast<float2*>(smem + P::kFixedSmem);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t pl = warp / Q, sub = warp % Q, tq = sub * 32 + lane;   // pipeline within the CTA, warp within the pipeline
+    const bool issuer = tq == 0;
+    uint64_t* full = bars + pl * S;
+    unsigned char* ring_in = rings + pl * P::kRing;
+    unsigned char* ring_out = ring_in + S * P::kTileIn;
+    TileDesc* desc_ring = reinterpret_cast<TileDesc*>(descs + pl * P::kDescBytes);
+    float2* win = reinterpret_cast<float2*>(wins + pl * P::kWinBytes);
+    auto pipe_sync = [&] { asm volatile("bar.sync %0, %1;" ::"r"(1u + pl), "r"((uint32_t)(Q * 32)) : "memory"); };
+
+    if (issuer) {
+        for (int s = 0; s < S; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pipe_sync();
+
+    const uint32_t pipe = blockIdx.x * P::kPipes + pl, npipes = gridDim.x * P::kPipes;
+    const unsigned char* gin = static_cast<const unsigned char*>(a.in);
+    unsigned char* gout = static_cast<unsigned char*>(a.out);
+
+    // the pipeline's first warp expands the work units and issues the loads; the descriptor reaches the others through shared memory
+    TileSrc<P> src;
+    if (sub == 0) src.init(a, lane, npipes);
+    auto issue_next = [&](uint32_t s) {   // all lanes of the pipeline's first warp
+        if (sub != 0) return;
+        TileDesc d;
+        const bool more = src.fetch(a, lane, d);
+        if (lane == 0) {
+            if (more) {
+                const uint32_t bytes = (d.nsamp - d.skip) * kInBps;
+                mbar_expect_tx(&full[s], bytes);
+                bulk_g2s(ring_in + s * P::kTileIn + d.skip * kInBps, gin + (size_t)(d.k0 + d.skip) * kInBps, bytes, &full[s]);
+            } else {
+                d.k0 = d.nsamp = d.seg = d.info = d.phase0 = d.period = d.skip = 0;
+                d.r = 0.0f;
+            }
+            desc_ring[s] = d;
+        }
+    };
+    for (uint32_t s = 0; s < (uint32_t)S; s++) issue_next(s);
+
+    // (optionally) one piece's table de-interleaved into shared memory
+    uint32_t plane_len = 0;
+    if (a.smem_piece != kNoPiece) {
+        const DevPiece sp = get_piece(a, a.smem_piece);
+        plane_len = P::plane_len(sp.period);
+        const float2* srct = a.tables + sp.tab;
+        for (uint32_t e = threadIdx.x; e < sp.period + (uint32_t)P::kRow; e += WARPS * 32)
+            tab_s[(e % G) * plane_len + e / G] = __ldg(srct + e % sp.period);
+    }
+    __syncthreads();
+
+    uint32_t pi = 0;
+    DevPiece p = get_piece(a, 0);
+    for (uint32_t i = 0;; i++) {
+        const uint32_t s = i % S;
+        pipe_sync();   // desc[s] is visible; the previous tile's readers of the window / scratch are done
+        const TileDesc d = desc_ring[s];
+        if (d.nsamp == 0) break;
+        const unsigned char* in_s = ring_in + s * P::kTileIn + sub * W::kTileIn;
+        unsigned char* out_s = ring_out + s * P::kTileOut + sub * W::kTileOut;
+        mbar_wait(&full[s], (i / S) & 1u);
+        uint32_t raw[U][4];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned char* srcp = in_s + (u * 32 + lane) * W::kGroupIn;
+            if constexpr (W::kGroupIn == 16) {
+                const uint4 w = *reinterpret_cast<const uint4*>(srcp);
+                raw[u][0] = w.x, raw[u][1] = w.y, raw[u][2] = w.z, raw[u][3] = w.w;
+            } else {
+                const uint2 w = *reinterpret_cast<const uint2*>(srcp);
+                raw[u][0] = w.x, raw[u][1] = w.y, raw[u][2] = 0, raw[u][3] = 0;
+            }
+        }
+        if (issuer) bulk_wait_read<S - 1>();   // the store that last read out[s] (tile i - S) has drained
+        pipe_sync();                           // every warp holds its sub-tile and the descriptor in registers
+        const uint32_t k0s = d.k0 + sub * kSub;   // first sample of this warp's sub-tile
+        bool refilled = false;
+        if (d.info & kColFlag) {
+            issue_next(s);
+            refilled = true;
+            if (d.info & kColFirst) {
+                eval_window_pipe<P>(win, d.r, d.period, d.phase0, tq);
+                pipe_sync();
+            }
+            stream_tile_column<W, IN, OUT, P::kWinPlane>(raw, out_s, win + sub * (kSub / G), d.info & 0xffu, lane);
+        } else {
+            const uint32_t k0 = d.k0;
+            if (k0 >= p.k_end || k0 < p.k_begin) {
+                pi = max(d.phase0, k0 >= p.k_end ? pi : 0u);
+                while (k0 >= piece_end(a, pi)) pi++;
+                p = get_piece(a, pi);
+            }
+            const bool fast = k0 + d.nsamp <= p.k_end;   // the whole pipeline tile inside one piece
+            if (fast) {
+                issue_next(s);
+                refilled = true;
+                if (p.tab == kNoTab)
+                    stream_tile_direct<W, IN, OUT>(raw, out_s, p, k0s, lane, win + sub * W::kPlateauEntries);
+                else if (pi == a.smem_piece)
+                    stream_tile<W, IN, OUT, kTabShared>(raw, out_s, p, k0s, tab_s, plane_len, lane);
+                else
+                    stream_tile<W, IN, OUT, kTabGlobal>(raw, out_s, p, k0s, a.tables + p.tab, 0, lane);
+            } else {
+                const uint32_t done_before = sub * kSub;
+                const uint32_t nsub = d.nsamp > done_before ? (d.nsamp - done_before < kSub ? d.nsamp - done_before : kSub) : 0u;
+                stream_tile_slow<W, IN, OUT>(a, pi, in_s, out_s, k0s, nsub, lane);
+                pipe_sync();   // the slow path reads in[s] itself: refill only when every warp is through
+            }
+        }
+        if (!refilled) issue_next(s);
+        fence_async_smem();
+        pipe_sync();
+        if (issuer) {
+            bulk_s2g(gout + (size_t)(d.k0 + d.skip) * kOutBps, ring_out + s * P::kTileOut + d.skip * kOutBps, (d.nsamp - d.skip) * kOutBps);
+            bulk_commit();
+        }
+    }
+    if (issuer) bulk_wait_all();
+
+    // sub-granule end of the buffer (fewer than kGran samples): pipeline 0's first warp mixes it straight from global memory
+    if (a.tail_begin < a.nsamples && pipe == 0 && sub == 0) {
         pi = find_piece(a, 0, a.tail_begin);
         p = get_piece(a, pi);
         for (uint32_t k = a.tail_begin + lane; k < a.nsamples; k += 32) {
