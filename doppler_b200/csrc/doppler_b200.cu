@@ -133,6 +133,7 @@ struct doppler_b200_ctx {
     uint64_t launches = 0;
     uint32_t small_max = kSmallMaxSamples;
     bool seg_alt = false;               // doppler_b200_tune: use StreamShape::seg_alt
+    uint32_t max_claim = dmix::kMaxClaim;   // doppler_b200_tune: work units claimed at once by the segmented kernels
     size_t tiny_host_bytes = kTinyHostBytes;
     // zero-copy per-block host path: completion flag in mapped host memory + CTA counter on the device
     uint32_t* done_flag = nullptr;      // host (pinned)
@@ -587,6 +588,7 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         a.tail_begin = tail_begin;
         a.smem_piece = smem_piece;
         a.plateau_scratch = shape.scratch_smem != 0;
+        a.max_claim = ctx->max_claim;
         // persistent: one CTA per SM, every warp an independent pipeline over interleaved work units
         if (grid_only) a.nunits = nsamp / shape.tile_samples;   // whole tiles; the lean loop mixes the ragged end itself
         const uint32_t want = (a.nunits + shape.pipes - 1) / shape.pipes;
@@ -1165,6 +1167,9 @@ int doppler_b200_tune(doppler_b200_ctx* ctx, int knob, uint64_t value)
         return DOPPLER_B200_OK;
     case DOPPLER_B200_TUNE_SEG_VARIANT:
         ctx->seg_alt = value != 0;
+        return DOPPLER_B200_OK;
+    case DOPPLER_B200_TUNE_MAX_CLAIM:
+        ctx->max_claim = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(value, 64));
         return DOPPLER_B200_OK;
     default:
         return fail(ctx, DOPPLER_B200_EINVAL, "unknown tuning knob %d", knob);

@@ -117,6 +117,7 @@ struct MixArgs {
     uint32_t tail_begin;      // samples [tail_begin, nsamples): the sub-granule end of the buffer
     uint32_t smem_piece;      // streaming kernel: piece whose table is staged in shared memory, or kNoPiece
     uint32_t plateau_scratch; // lean kernel: 1 when the launch carries a per-warp plateau scratch (direct-evaluation shape)
+    uint32_t max_claim;       // segmented kernels: most work units claimed at once (guided self-scheduling), >= 1
     DevPiece inl[kInlinePieces];
     DevSeg inl_segs[kInlineSegs];
 };
@@ -804,7 +805,7 @@ struct TileIter {
 constexpr uint32_t kMaxClaim = 8;
 template <typename C>
 struct TileSrc {
-    uint32_t nunits, npipes;
+    uint32_t nunits, npipes, max_claim;
     uint32_t pending, pending_cnt;     // pending (lane 0): first unit of the chunk claimed ahead; pending_cnt: its size
     uint32_t u_cur, u_end;             // units left in the current chunk
     uint32_t seg, seg_unit_end;        // current segment
@@ -819,13 +820,14 @@ struct TileSrc {
     {
         const uint32_t left = claimed < nunits ? nunits - claimed : 0u;
         const uint32_t c = left / (4u * npipes);
-        return c < 1u ? 1u : (c > kMaxClaim ? kMaxClaim : c);
+        return c < 1u ? 1u : (c > max_claim ? max_claim : c);
     }
 
     __device__ __forceinline__ void init(const MixArgs& a, uint32_t lane, uint32_t npipes_)
     {
         nunits = a.nunits;
         npipes = npipes_;
+        max_claim = a.max_claim ? a.max_claim : 1u;
         pending_cnt = claim_size(0);
         pending = lane == 0 ? atomicAdd(a.unit_counter, pending_cnt) : 0u;
         u_cur = u_end = 0;
