@@ -133,7 +133,8 @@ struct doppler_b200_ctx {
     uint64_t launches = 0;
     uint32_t small_max = kSmallMaxSamples;
     bool seg_alt = false;               // doppler_b200_tune: use StreamShape::seg_alt
-    uint32_t max_claim = dmix::kMaxClaim;   // doppler_b200_tune: work units claimed at once by the segmented kernels
+    uint32_t max_claim = 1;             // work units claimed at once by the segmented kernels (doppler_b200_tune; chunks of up to 8
+                                        // lost the A/B by 6-15 %, profiles/r02_ab_seg.jsonl)
     size_t tiny_host_bytes = kTinyHostBytes;
     // zero-copy per-block host path: completion flag in mapped host memory + CTA counter on the device
     uint32_t* done_flag = nullptr;      // host (pinned)
@@ -228,10 +229,11 @@ KernShape make_pipe_shape()
 }
 
 // (WARPS, S, U) of the segmented kernel per type pair; the host walk of the work decomposition
-// (doppler_b200_plan_tiles_trace) instantiates the same configurations.  i16 -> i16 (issue-bound at 8 bytes per sample)
-// runs 4-warp pipelines; `SegI16I16W` is the per-warp form of round 1, kept selectable (doppler_b200_tune) for A/B runs.
-using SegI16I16 = dmix::PipeCfg<0, 0, SEG_I16I16, 4>;
-using SegI16I16W = dmix::StreamCfg<0, 0, SEG_I16I16>;
+// (doppler_b200_plan_tiles_trace) instantiates the same configurations.  The 4-warp pipelines of mix_pipe_kernel
+// (i16 -> i16) lost the interleaved A/B against the per-warp pipelines (COLUMN 0.92 vs 0.95, cfg3 0.84 vs 0.90 of peak,
+// profiles/r02_ab_seg.jsonl: the named barriers cost more than the shared issue work saves) and stay selectable
+// through doppler_b200_tune for such comparisons only.
+using SegI16I16 = dmix::StreamCfg<0, 0, SEG_I16I16>;
 using SegI16F32 = dmix::StreamCfg<0, 1, SEG_I16F32>;
 using SegF32I16 = dmix::StreamCfg<1, 0, SEG_F32I16>;
 using SegF32F32 = dmix::StreamCfg<1, 1, SEG_F32F32>;
@@ -243,7 +245,7 @@ const StreamShape& shape_for(int in, int out)
     // isolated launches prefer (24,2,2) for f32->i16, r01_tune_stream_smemtab_fmul2.jsonl).
     // direct shapes: profiles/r01_tune_direct_linear.jsonl
     static const StreamShape shapes[2][2] = {
-        {{make_shape<0, 0, 20, 2, 2, false>(), make_pipe_shape<0, 0, SEG_I16I16, 4>(), make_shape<0, 0, SEG_I16I16, true>(),
+        {{make_shape<0, 0, 20, 2, 2, false>(), make_shape<0, 0, SEG_I16I16, true>(), make_pipe_shape<0, 0, SEG_I16I16, 4>(),
           make_shape<0, 0, 12, 2, 6, false, true>()},
          {make_shape<0, 1, 20, 3, 2, false>(), make_shape<0, 1, SEG_I16F32, true>(), make_shape<0, 1, SEG_I16F32, true>(),
           make_shape<0, 1, 16, 2, 4, false, true>()}},

@@ -797,11 +797,10 @@ struct TileIter {
 
 #if defined(__CUDACC__)
 // Device tile source: every member is executed by ALL lanes of the warp (warp-convergent); results are warp-uniform.
-// Units are claimed in CHUNKS of consecutive units whose size follows the work that is left (guided self-scheduling):
-// up to kMaxClaim while the launch is young -- consecutive units mostly share a segment, so the segment lookup (two to
-// three dependent global loads) and the atomic are paid once per chunk -- down to single units near the end, where
-// balance between the pipelines matters.  The claim for the NEXT chunk is issued when a chunk starts, so its latency
-// hides behind the chunk's tiles.
+// Units are claimed one at a time (MixArgs::max_claim = 1), the claim for the NEXT unit issued when a unit starts so that its
+// latency hides behind the unit's tiles.  Larger, guided claims (up to max_claim consecutive units while the launch is young,
+// single units near the end) save atomics and segment lookups but measured 6-15 % SLOWER (profiles/r02_ab_seg.jsonl); the
+// mechanism stays for such A/B runs.
 constexpr uint32_t kMaxClaim = 8;
 template <typename C>
 struct TileSrc {
@@ -1055,7 +1054,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mix_stream_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pipelines of Q warps (round 2, i16 -> i16).  At 8 bytes per sample the segmented kernel is bound by instruction issue,
+// Pipelines of Q warps (round 2 experiment, NOT the product path: it lost the A/B, see doppler_b200.cu).  At 8 bytes per sample the segmented kernel is bound by instruction issue,
 // and a third of what it issues is per-TILE work: barrier wait and tile loads, unit expansion and bulk-load issue, fence and
 // bulk-store issue -- ~150 instructions per 512-sample tile (ncu source view, profiles/r02_ncu_cfg3_before.txt).  Here Q
 // warps share one pipeline: one bulk load brings a tile Q times as large, every warp multiplies its own sub-tile exactly

@@ -52,7 +52,7 @@ def oracle():
     return oracle_lib.Oracle()
 
 
-@pytest.fixture(scope="session", params=["default", "bulk-async kernels only", "bulk-async, per-warp segmented kernel"])
+@pytest.fixture(scope="session", params=["default", "bulk-async kernels only", "bulk-async, 4-warp segmented pipelines"])
 def mixer(request):
     """The suite runs twice: with the product's thresholds (short inputs take the latency-shaped small kernel and the
     zero-copy host path) and with both disabled, so that every input -- however short or ragged -- also goes through
@@ -60,6 +60,6 @@ def mixer(request):
     import doppler_b200
     m = doppler_b200.Mixer(0)
     if request.param != "default":
-        m.tune(small_max_samples=0, tiny_host_bytes=0, seg_variant=int("per-warp" in request.param))
+        m.tune(small_max_samples=0, tiny_host_bytes=0, seg_variant=int("4-warp" in request.param))
     yield m
     m.close()

@@ -31,7 +31,7 @@ def main():
     for sv, mc in itertools.product((0, 1), (8, 1)):
         m = doppler_b200.Mixer(0)
         m.tune(seg_variant=sv, max_claim=mc)
-        variants[f"{'per-warp' if sv else 'product'} claim<={mc}"] = m
+        variants[f"{'4-warp pipelines' if sv else 'per-warp pipelines'} claim<={mc}"] = m
     cases = []
     n = 256_000_000
     for it, ot in ((I16, I16), (I16, F32), (F32, I16), (F32, F32)):
