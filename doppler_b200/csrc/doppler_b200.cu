@@ -131,6 +131,7 @@ struct doppler_b200_ctx {
     cudaStream_t meta_stream = nullptr;   // metadata uploads run here, beside the previous launch's kernel
     std::string err;
     uint64_t launches = 0;
+    std::vector<const void*> configured;   // kernels whose dynamic shared-memory limit has been raised
     uint32_t small_max = kSmallMaxSamples;
     bool seg_alt = false;               // doppler_b200_tune: use StreamShape::seg_alt
     uint32_t max_claim = 1;             // work units claimed at once by the segmented kernels (doppler_b200_tune; chunks of up to 8
@@ -656,6 +657,12 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
             const uint32_t ctas = one_cta ? 1u : std::min<uint32_t>((groups + per_cta - 1) / per_cta, (uint32_t)ctx->sm_count * 8u);   // one resident wave
             small_kernel_for(intype, outtype, wide)<<<ctas, dmix::kSmallThreads, 0, s>>>(a, done ? *done : dmix::SmallDone{nullptr, nullptr, 0});
         } else {
+            const void* kfn = reinterpret_cast<const void*>(shape.kern);
+            if (std::find(ctx->configured.begin(), ctx->configured.end(), kfn) == ctx->configured.end()) {
+                CUDA_TRY(ctx, cudaFuncSetAttribute(shape.kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(shape.fixed_smem + shape.table_bytes(shape.smem_tab_entries))));
+                ctx->configured.push_back(kfn);
+            }
             shape.kern<<<grid, shape.warps * 32, smem, s>>>(a);
         }
         CUDA_TRY(ctx, cudaGetLastError());
@@ -1065,14 +1072,8 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&ctx->meta_stream, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->tables_ready, cudaEventDisableTiming);
-    for (int i = 0; i < 2 && e2 == cudaSuccess; i++)
-        for (int o = 0; o < 2 && e2 == cudaSuccess; o++) {
-            const StreamShape& sh = shape_for(i, o);
-            for (const KernShape* k : {&sh.grid, &sh.seg, &sh.seg_alt, &sh.direct})
-                if (e2 == cudaSuccess)
-                    e2 = cudaFuncSetAttribute(k->kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)(k->fixed_smem + k->table_bytes(k->smem_tab_entries)));
-        }
+    // (the kernels' shared-memory attributes are set on first use, launch_mix: configuring all of them here loads every
+    //  kernel of the module, which a CLI run over a second of IQ never needs)
     if (e2 != cudaSuccess) {
         fail(nullptr, DOPPLER_B200_ECUDA, "context setup failed: %s", cudaGetErrorString(e2));
         delete ctx;
