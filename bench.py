@@ -204,8 +204,11 @@ def run_reference(args):
                                    f"{threads} threads), not the {SECONDS_PER_GPU * FS} of the GPU arm's step; the metric is a rate")
     configs = None
     if not args.no_configs:
-        cols = cpu_config_columns(threads)
-        configs = {"note": "CPU columns only: the oracle (reference CPU path) on a bounded sample of every BASELINE config", **cols}
+        try:
+            cols = cpu_config_columns(threads)
+            configs = {"note": "CPU columns only: the oracle (reference CPU path) on a bounded sample of every BASELINE config", **cols}
+        except Exception as e:   # noqa: BLE001
+            configs = {"error": f"{type(e).__name__}: {e}"[:300]}
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_tot / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -719,12 +722,22 @@ def main():
     if not args.no_configs:
         configs = {"cfg2": "the headline of this line (value / roofline / e2e)"}
         t_c = time.time()
-        configs["cfg3"] = run_cfg3(mixer, tstream, D, peak, oracle_threads)
-        configs["cfg4"] = run_cfg4(mixer, tstream, D, peak, oracle_threads)
-        configs["cfg5"] = run_cfg5(mixer, tstream, D, peak)
-        configs["f4_mix_decimate"] = run_f4(mixer, tstream, D, peak)
+
+        def guarded(name, fn, *a):
+            """A config that fails reports its error in place; it never costs the line its headline.  (Every rank runs the same
+            code on the same inputs, so a failure is collective and the ranks stay in step.)"""
+            try:
+                configs[name] = fn(*a)
+            except Exception as e:   # noqa: BLE001
+                configs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.synchronize()
+
+        guarded("cfg3", run_cfg3, mixer, tstream, D, peak, oracle_threads)
+        guarded("cfg4", run_cfg4, mixer, tstream, D, peak, oracle_threads)
+        guarded("cfg5", run_cfg5, mixer, tstream, D, peak)
+        guarded("f4_mix_decimate", run_f4, mixer, tstream, D, peak)
         if rank == 0:
-            configs["cfg1"] = run_cfg1_cli(oracle_threads)
+            guarded("cfg1", run_cfg1_cli, oracle_threads)
         configs["gpu_seconds"] = time.time() - t_c
 
     mixer.close()
@@ -733,18 +746,26 @@ def main():
         threads = host_threads()
         if configs is not None:   # CPU columns beside every config (rank 0's host cores; the other ranks are idle here)
             t_c = time.time()
-            cols = cpu_config_columns(threads)
-            for k in ("cfg1", "cfg3", "cfg4"):
-                configs[k].update(cols[k])
-            for k, v in cols["cfg5"].items():
-                configs["cfg5"][k].update(v)
+            try:
+                cols = cpu_config_columns(threads)
+                for k in ("cfg1", "cfg3", "cfg4"):
+                    if isinstance(configs.get(k), dict):
+                        configs[k].update(cols[k])
+                for k, v in cols["cfg5"].items():
+                    if isinstance(configs.get("cfg5"), dict) and isinstance(configs["cfg5"].get(k), dict):
+                        configs["cfg5"][k].update(v)
+            except Exception as e:   # noqa: BLE001
+                configs["cpu_columns_error"] = f"{type(e).__name__}: {e}"[:300]
             configs["cpu_seconds"] = time.time() - t_c
             configs["cpu_note"] = ("cpu_msps_*: the oracle (reference CPU path; the reference is single-threaded, the all-core figure runs "
                                    "contiguous time slices on every host thread) on a bounded in-memory sample of the same config")
         if world == 1 and not args.no_cpu_baseline:
-            base, _, _ = cpu_baseline(threads)
-            one, _, _ = cpu_baseline(1, seconds_target=4.0)
-            base["value_1core"] = one["value"]
+            try:
+                base, _, _ = cpu_baseline(threads)
+                one, _, _ = cpu_baseline(1, seconds_target=4.0)
+                base["value_1core"] = one["value"]
+            except Exception as e:   # noqa: BLE001
+                base = {"error": f"{type(e).__name__}: {e}"[:300]}
         # DRAM traffic of one launch at THIS launch size, by ncu, after every timed region (one GPU only: ncu serialises)
         tr = None
         if world == 1 and not args.no_ncu:

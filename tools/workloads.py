@@ -124,6 +124,8 @@ def cpu_columns(oracle, threads, budget_s=1.0):
     out = {}
 
     def both(intype, outtype, fs, shift=None, shifts=None, seed=0, cap=1 << 62):
+        if shifts is not None:   # never more samples than the schedule covers (many-core boxes ask for a lot)
+            cap = min(cap, (len(shifts) - 1) * (8192 // BPS[intype]))
         one = cpu_rate(oracle, intype, outtype, fs, min(1 << 20, cap) // 2048 * 2048, 1, shift, shifts, seed)
         n = int(min(cap, max(1 << 21, one * 1e6 * budget_s * threads * 0.6))) // 2048 * 2048
         allc = cpu_rate(oracle, intype, outtype, fs, n, threads, shift, shifts, seed)
