@@ -125,10 +125,17 @@ def test_cfg4_track_f32_one_slice_of_the_8_gpu_job(oracle, mixer):
     mixer.synchronize()
     assert sn == slicing.seed_blocks(shifts, F32, fs, end)
     rng = np.random.default_rng(4)
-    for b, e in _windows(rng, n, bs, 20):
+    for b, e in _windows(rng, n, bs, 12):
         want, _ = oracle.mix_blocks(x[b * 8:e * 8].cpu().numpy(), F32, F32, sl[b // bs:], fs,
                                     samplenum=slicing.seed_blocks(shifts, F32, fs, begin + b))
         assert _same(y[b * 8:e * 8].cpu().numpy(), want, F32), (b, e)
+    # 2^24 samples straddling every slice boundary = the last 2^23 samples of a slice and the first 2^23 of the
+    # next; here both ends of this slice (bench.py does the same for every slice of the job, plus the first and last second)
+    import os
+    from tools import workloads as W
+    half = 1 << 23
+    ok, checked, _ = W.check_windows(oracle, x, y, F32, F32, shifts, fs, begin, [(0, half), ((n - half) // bs * bs, n)], len(os.sched_getaffinity(0)))
+    assert ok and checked >= 2 * half
     h = (n // 2) // bs * bs
     y2 = torch.empty((n - h) * 8, dtype=torch.uint8, device="cuda")
     mixer.mix_blocks_dev(x.data_ptr() + h * 8, (n - h) * 8, F32, F32, sl[h // bs:], fs, slicing.seed_blocks(shifts, F32, fs, begin + h),
