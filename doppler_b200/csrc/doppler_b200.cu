@@ -26,6 +26,7 @@
 
 #include "../../include/doppler_b200.h"
 #include "mixer_kernels.cuh"
+#include "decimate_kernels.cuh"
 #include "plan.h"
 
 // (WARPS, S, U) of the segmented kernel per type pair, chosen on B200 (profiles/r01_seg_tune.md: warps
@@ -134,6 +135,7 @@ struct doppler_b200_ctx {
     std::vector<const void*> configured;   // kernels whose dynamic shared-memory limit has been raised
     uint32_t small_max = kSmallMaxSamples;
     bool seg_alt = false;               // doppler_b200_tune: use StreamShape::seg_alt
+    bool decim_generic = false;         // doppler_b200_tune: the fused decimator always takes the generic kernel
     uint32_t max_claim = 1;             // work units claimed at once by the segmented kernels (doppler_b200_tune; chunks of up to 8
                                         // lost the A/B by 6-15 %, profiles/r02_ab_seg.jsonl)
     size_t tiny_host_bytes = kTinyHostBytes;
@@ -1171,6 +1173,9 @@ int doppler_b200_tune(doppler_b200_ctx* ctx, int knob, uint64_t value)
     case DOPPLER_B200_TUNE_SEG_VARIANT:
         ctx->seg_alt = value != 0;
         return DOPPLER_B200_OK;
+    case DOPPLER_B200_TUNE_DECIM_VARIANT:
+        ctx->decim_generic = value != 0;
+        return DOPPLER_B200_OK;
     case DOPPLER_B200_TUNE_MAX_CLAIM:
         ctx->max_claim = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(value, 64));
         return DOPPLER_B200_OK;
@@ -1274,6 +1279,9 @@ struct doppler_b200_decim {
     cudaEvent_t hist_ready = nullptr;          // the history of the latest call has been written
     cudaStream_t hist_stream = nullptr;
     bool hist_event_valid = false;
+    // register-blocked kernel (decimate_kernels.cuh): tap layout and walk segments of this filter, or fast_ok == false
+    bool fast_ok = false;
+    dmix::DecimFastArgs fast;
 };
 
 namespace {
@@ -1282,6 +1290,43 @@ constexpr uint32_t kDecimMaxTaps = 4096;
 constexpr uint32_t kDecimStageSlots = 5120;   // mixed samples staged per CTA step (40 KB)
 
 using DecimKernel = void (*)(const dmix::DecimArgs);
+using DecimFastKernel = void (*)(const dmix::DecimFastArgs);
+
+// Register-blocked kernel: the filter's tap layout per walk position and the walk's segments (decimate_kernels.cuh).  The
+// envelope: the layout fits the kernel parameters, and at least one warp's worth of output-owning threads fits the stage.
+void decim_fast_setup(doppler_b200_decim* d, const float* taps)
+{
+    constexpr uint32_t R = dmix::kDfR;
+    const uint32_t M = d->M, ntaps = d->ntaps, ntq = (R - 1) * M + ntaps;
+    d->fast_ok = false;
+    if (M > 64 || ntq > (uint32_t)dmix::kDfMaxTq) return;
+    dmix::DecimFastArgs& f = d->fast;
+    memset(&f, 0, sizeof f);
+    // a CTA step stages lead (<= 3) + (4 * tb - 1) * M + ntaps samples (+ one 16-byte group of slack), one padding slot per 4M
+    uint32_t tb = dmix::kDfThreads;
+    for (; tb >= 32; tb -= 32) {
+        const uint64_t count = 3 + (uint64_t)(R * tb - 1) * M + ntaps + 4;
+        if (count + count / (R * M) + 2 <= dmix::kDfStageSlots) break;
+    }
+    if (tb < 32) return;
+    f.tb = tb;
+    for (uint32_t u = 0; u < ntq; u++)
+        for (uint32_t k = 0; k < R; k++) {
+            const int64_t t = (int64_t)u - (int64_t)(R - 1 - k) * M;
+            const float h = (t >= 0 && t < (int64_t)ntaps) ? taps[t] : 0.0f;
+            uint32_t b;
+            memcpy(&b, &h, 4);
+            f.tq[u][k] = (uint64_t)b | ((uint64_t)b << 32);
+        }
+    // output k is active at walk positions [(3 - k) * M, (3 - k) * M + ntaps): the sorted bounds cut the walk into 7 segments
+    for (uint32_t k = 0; k < R; k++) {
+        f.cuts[k] = k * M;
+        f.cuts[R + k] = k * M + ntaps;
+    }
+    std::sort(f.cuts, f.cuts + 2 * R);
+    f.shape = std::min<uint32_t>(3, (ntaps - 1) / M);
+    d->fast_ok = true;
+}
 
 // One device-resident call of the fused stage: `runs` over n samples at d_in; outputs to d_out.  Asynchronous on `s`.
 int decimate_launch(doppler_b200_decim* dec, const void* d_in, uint64_t n, int intype, int outtype, const std::vector<dplan::Run>& runs,
@@ -1354,7 +1399,28 @@ int decimate_launch(doppler_b200_decim* dec, const void* d_in, uint64_t n, int i
     const size_t smem = ((dec->ntaps * 4 + 15) & ~(size_t)15) + slots * sizeof(float2);
     static const DecimKernel kern[2][2] = {{dmix::mix_decimate_kernel<0, 0>, dmix::mix_decimate_kernel<0, 1>},
                                            {dmix::mix_decimate_kernel<1, 0>, dmix::mix_decimate_kernel<1, 1>}};
-    if (nout) {
+#define DF_SHAPES(I, O) {dmix::mix_decimate_fast_kernel<I, O, 0>, dmix::mix_decimate_fast_kernel<I, O, 1>, \
+                         dmix::mix_decimate_fast_kernel<I, O, 2>, dmix::mix_decimate_fast_kernel<I, O, 3>}
+    static const DecimFastKernel fkern[2][2][4] = {{DF_SHAPES(0, 0), DF_SHAPES(0, 1)}, {DF_SHAPES(1, 0), DF_SHAPES(1, 1)}};
+#undef DF_SHAPES
+    if (nout && dec->fast_ok && !ctx->decim_generic && ((((uintptr_t)d_in) | ((uintptr_t)d_out)) & 15) == 0) {
+        // register-blocked kernel: 4 consecutive outputs per thread, taps in the kernel parameters (decimate_kernels.cuh)
+        constexpr uint32_t R = dmix::kDfR;
+        dmix::DecimFastArgs& f = dec->fast;
+        f.d = a;
+        f.lead = (uint32_t)((((int64_t)i0 - (int64_t)(dec->ntaps - 1)) % 4 + 4) % 4);
+        f.ctop = f.lead + (dec->ntaps - 1) + (R - 1) * M;
+        const uint64_t count = f.lead + (uint64_t)(R * f.tb - 1) * M + dec->ntaps + 4;
+        const size_t fsmem = (size_t)(count + count / (R * M) + 2) * sizeof(float2);
+        const uint64_t steps = (nout + (uint64_t)R * f.tb - 1) / ((uint64_t)R * f.tb);
+        const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(2048 / dmix::kDfThreads, (size_t)(227 * 1024) / (fsmem + 1024)));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(steps, (uint64_t)ctx->sm_count * per_sm);
+        const DecimFastKernel fk = fkern[intype][outtype][f.shape];
+        CUDA_TRY(ctx, cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dmix::kDfStageSlots * sizeof(float2))));
+        fk<<<grid, dmix::kDfThreads, fsmem, s>>>(f);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    } else if (nout) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>((nout + ot - 1) / ot, (uint64_t)ctx->sm_count * 8);
         CUDA_TRY(ctx, cudaFuncSetAttribute(kern[intype][outtype], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern[intype][outtype]<<<grid, dmix::kDecimThreads, smem, s>>>(a);
@@ -1484,6 +1550,7 @@ int doppler_b200_decim_create(doppler_b200_ctx* ctx, const float* taps, uint32_t
         if (e == cudaSuccess) e = cudaMemset(d->d_hist[i], 0, hb);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->hist_ready, cudaEventDisableTiming);
+    decim_fast_setup(d, taps);
     if (e != cudaSuccess) {
         fail(ctx, DOPPLER_B200_ECUDA, "decimator setup failed: %s", cudaGetErrorString(e));
         doppler_b200_decim_destroy(d);

@@ -66,8 +66,10 @@ class Mixer:
     def synchronize(self):
         self._check(self._lib.doppler_b200_synchronize(self._ctx))
 
-    def tune(self, small_max_samples=None, tiny_host_bytes=None, seg_variant=None, max_claim=None):
+    def tune(self, small_max_samples=None, tiny_host_bytes=None, seg_variant=None, max_claim=None, decim_variant=None):
         """Thresholds between code paths (doppler_b200_tune); results are identical on every path."""
+        if decim_variant is not None:
+            self._check(self._lib.doppler_b200_tune(self._ctx, 5, int(decim_variant)))
         if max_claim is not None:
             self._check(self._lib.doppler_b200_tune(self._ctx, 4, int(max_claim)))
         if seg_variant is not None:

@@ -57,10 +57,25 @@ def test_oracle_decimator_i16_egress_saturates_like_the_mixer(oracle):
 
 # ---- GPU: parity with the specification ---------------------------------------------------------------
 
+@pytest.fixture(params=["register-blocked kernel", "generic kernel"])
+def decim_variant(request, mixer):
+    """Both forms of the fused stage (doppler_b200_tune DECIM_VARIANT): the register-blocked kernel wherever the filter fits its
+    envelope, and the generic kernel for every filter."""
+    mixer.tune(decim_variant=int(request.param == "generic kernel"))
+    yield request.param
+    mixer.tune(decim_variant=0)
+
+
+# (M, ntaps): every filter shape of the register-blocked kernel -- ntaps <= M, <= 2M, <= 3M, > 3M, ties at the multiples --
+# odd and even M, M = 1, a stage of one warp (M = 64), and filters outside its envelope (M > 64, 3M + ntaps > 224)
+FILTERS = [(8, 33), (4, 64), (3, 17), (1, 9), (25, 101), (2, 1), (8, 20), (8, 12), (8, 5), (8, 8), (8, 16), (8, 24), (5, 15),
+           (7, 14), (16, 49), (64, 30), (6, 200), (10, 4), (100, 40), (2, 300)]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("intype,outtype", [(I16, I16), (I16, F32), (F32, I16), (F32, F32)])
-@pytest.mark.parametrize("M,ntaps", [(8, 33), (4, 64), (3, 17), (1, 9), (25, 101), (2, 1)])
-def test_mix_decimate_matches_oracle(oracle, mixer, intype, outtype, M, ntaps):
+@pytest.mark.parametrize("M,ntaps", FILTERS)
+def test_mix_decimate_matches_oracle(oracle, mixer, decim_variant, intype, outtype, M, ntaps):
     rng = np.random.default_rng(M * 1000 + ntaps)
     taps = lowpass(ntaps, 0.4 / M) if ntaps > 1 else np.array([0.75], dtype=np.float32)
     dec = doppler_b200.Decimator(mixer, taps, M)
@@ -80,7 +95,7 @@ def test_mix_decimate_matches_oracle(oracle, mixer, intype, outtype, M, ntaps):
 
 
 @pytest.mark.gpu
-def test_mix_blocks_decimate_and_chunked_host_pipeline(oracle, mixer):
+def test_mix_blocks_decimate_and_chunked_host_pipeline(oracle, mixer, decim_variant):
     """A per-block shift schedule, and an input long enough for several 32 MiB pipeline chunks (history handed from slot to slot)."""
     rng = np.random.default_rng(77)
     M, taps = 8, lowpass(48, 0.05)
@@ -104,7 +119,7 @@ def test_mix_blocks_decimate_and_chunked_host_pipeline(oracle, mixer):
 
 
 @pytest.mark.gpu
-def test_mix_decimate_dev_and_argument_checks(oracle, mixer):
+def test_mix_decimate_dev_and_argument_checks(oracle, mixer, decim_variant):
     torch = pytest.importorskip("torch")
     rng = np.random.default_rng(9)
     M, taps = 5, lowpass(31, 0.08)
