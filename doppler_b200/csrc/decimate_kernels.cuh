@@ -22,9 +22,12 @@
 //   * the walk is cut into seven segments of constant active output range [klo, khi] (compile-time per filter shape, bounds from
 //     the host), so the inner loops carry no predicates and issue exactly ntaps multiply-adds per output;
 //   * lanes read y at a stride of 4M samples; one padding slot per 4M samples (slot(j) = j + j / 4M) makes the stride odd in
-//     8-byte units, which is bank-conflict free.  The walk crosses a padding slot at warp-uniform positions.
-// Phase A of a CTA step (mix the samples the step's outputs need into shared memory) runs 16-byte global loads, four in flight
-// per thread, and table phasors through L1; phase B is the walk.  Several CTAs per SM overlap each other's phases.
+//     8-byte units, which is bank-conflict free.  The walk crosses a padding slot at warp-uniform positions that depend only on
+//     the launch, so the host cuts the segments there too: the device runs a list of (length, skip) runs.
+// Phase A of a CTA step (mix the samples the step's outputs need into shared memory) runs 16-byte global loads through two
+// register buffers (the next batch is in flight while one is mixed; the first batch of the next step while this step walks)
+// against a copy of the piece's phasor table in shared memory; phase B is the walk.  Several CTAs per SM overlap each other's
+// phases.  CTAs are 256 threads, or 128 where a stage of 256 * 4 outputs would not fit (M > 8).
 //
 // Launches outside the envelope (too many taps for the parameter block, M > 64, unaligned buffers) and pieces without a table
 // keep the generic paths: mix_decimate_kernel, or the per-sample loop of phase A below.
@@ -35,18 +38,33 @@
 namespace dmix {
 
 constexpr int kDfR = 4;                 // outputs per thread
-constexpr int kDfThreads = 256;
+constexpr int kDfMaxThreads = 256;
 constexpr int kDfMaxTq = 224;           // walk positions (3M + ntaps) the parameter block holds
-constexpr uint32_t kDfStageSlots = 8448;   // shared-memory slots (8 B) of one CTA step: 66 KB, three CTAs per SM
+constexpr int kDfMaxRuns = 72;          // 7 segments + one cut per padding slot crossed (at most 224 / 4 + 1)
+constexpr uint32_t kDfStageSlots = 8448;   // shared-memory slots (8 B) of one CTA step by default: 66 KB, three CTAs per SM
+constexpr uint32_t kDfTabCap = 1024;       // phasor-table entries (8 B) a CTA keeps in shared memory; longer tables are read through L1
+
+struct DfRun {
+    uint16_t n;      // walk positions of this run
+    uint16_t skip;   // padding slots crossed after it (0 or 1)
+};
+
+struct alignas(16) DfTaps {
+    uint64_t h[kDfR];   // h[k] = (tap, tap) of output k at this walk position: tap index u - (3 - k) * M, 0 outside the filter
+};
 
 struct DecimFastArgs {
     DecimArgs d;
-    uint32_t tb;          // threads of a CTA that own outputs (a multiple of 32): a CTA step makes 4 * tb outputs
+    uint32_t tb;          // threads of a CTA that own outputs (a multiple of 32, <= the CTA size): a CTA step makes 4 * tb outputs
     uint32_t lead;        // staged sample 0 is call-relative sample i0 - lead, so that it is a multiple of 4 (16-byte loads)
-    uint32_t ctop;        // staged index, relative to a thread's base tid * 4M, of walk position 0: lead + ntaps - 1 + 3M
+    uint32_t slot0;       // slot, relative to a thread's base tid * (4M + 1), of walk position 0: c0 + c0 / 4M, c0 = lead + ntaps - 1 + 3M
     uint32_t shape;       // min(3, (ntaps - 1) / M): selects the kernel instantiation
-    uint32_t cuts[8];     // {0, M, 2M, 3M, ntaps, M + ntaps, 2M + ntaps, 3M + ntaps} sorted: segment i = [cuts[i], cuts[i+1])
-    uint64_t tq[kDfMaxTq][kDfR];   // tq[u][k] = (h[t], h[t]) with t = u - (3 - k) * M, 0 outside the filter
+    uint32_t rm_magic;    // j / 4M == umulhi(j, rm_magic) for the staged indices of a step
+    uint32_t tab_cap;     // phasor-table entries the launch reserves in shared memory (0: tables stay in global memory)
+    uint32_t nruns[8];    // runs of segment i (consecutive in `runs`); segment i = [cuts[i], cuts[i+1]) of the sorted bounds
+                          // {0, M, 2M, 3M, ntaps, M + ntaps, 2M + ntaps, 3M + ntaps}
+    DfRun runs[kDfMaxRuns];
+    DfTaps tq[kDfMaxTq];
 };
 
 __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c)
@@ -55,40 +73,55 @@ __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
-
-// walk positions [u0, u1) with outputs KLO .. KHI active; p = this thread's slot of position u0, cm = how many more positions
-// precede the next padding slot (warp-uniform)
-template <int KLO, int KHI>
-__device__ __forceinline__ void df_walk(const DecimFastArgs& A, const uint64_t*& p, uint32_t& cm, uint32_t rm, uint32_t u0, uint32_t u1,
-                                        uint64_t (&acc)[kDfR])
+// 32-bit shared-window addresses: no generic-to-shared conversion inside the loops
+__device__ __forceinline__ uint64_t lds_u64(uint32_t addr)
 {
-    while (u0 < u1) {
-        const uint32_t left = u1 - u0;
-        const bool cross = cm < left;
-        const uint32_t n = cross ? cm + 1u : left;
-        const uint32_t ue = u0 + n;
-#pragma unroll 4
-        for (uint32_t u = u0; u < ue; ++u) {
-            const uint64_t y = *p;
-            --p;
+    uint64_t v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32x2(uint32_t addr, float2 v)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// n walk positions from u on, outputs KLO .. KHI active; p = shared address of this thread's slot of position u
+// (u is a signed int so that the tap addresses of an unrolled body fold into immediate offsets of one uniform register)
+template <int KLO, int KHI>
+__device__ __forceinline__ void df_walk(const DecimFastArgs& A, uint32_t& p, int& u, uint32_t n, uint64_t (&acc)[kDfR])
+{
+    for (; n >= 4u; n -= 4u) {
+        uint64_t y[4];
 #pragma unroll
-            for (int k = KLO; k <= KHI; ++k) acc[k] = fma_f32x2(A.tq[u][k], y, acc[k]);
+        for (int i = 0; i < 4; i++) y[i] = lds_u64(p - 8u * i);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int k = KLO; k <= KHI; ++k) acc[k] = fma_f32x2(A.tq[u + i].h[k], y[i], acc[k]);
         }
-        u0 = ue;
-        if (cross) {
-            --p;   // the padding slot
-            cm = rm - 1u;
-        } else {
-            cm -= n;
-        }
+        u += 4;
+        p -= 32u;
+    }
+    for (; n; --n) {
+        const uint64_t y = lds_u64(p);
+#pragma unroll
+        for (int k = KLO; k <= KHI; ++k) acc[k] = fma_f32x2(A.tq[u].h[k], y, acc[k]);
+        ++u;
+        p -= 8u;
     }
 }
 
-// The walk's seven segments.  Output k is active at positions [(3 - k) * M, (3 - k) * M + ntaps); the eight bounds sorted
-// are the segments' cuts (the host sorts them: DecimFastArgs::cuts), and which outputs are active between two neighbouring
-// cuts depends only on SHAPE = min(3, (ntaps - 1) / M) -- so the ranges are compile-time and the dispatch is straight-line
-// code (a switch on a run-time range compiles to an indexed branch, after which ptxas no longer keeps the tap reads on the
-// uniform datapath).  Ties between cuts make empty segments.
+// The walk's seven segments.  Output k is active at positions [(3 - k) * M, (3 - k) * M + ntaps); the eight bounds sorted are
+// the segments' cuts, and which outputs are active between two neighbouring cuts depends only on
+// SHAPE = min(3, (ntaps - 1) / M) -- so the ranges are compile-time and the dispatch is straight-line code (a switch on a
+// run-time range compiles to an indexed branch, after which ptxas no longer keeps the tap reads on the uniform datapath).
+// Ties between cuts make empty segments.
 template <int SHAPE, int I>
 struct DfRange {
     //                                   segment:      0  1  2  3  4  5  6
@@ -100,56 +133,139 @@ struct DfRange {
     static constexpr int hi = SHAPE == 3 ? hi3[I] : SHAPE == 2 ? hi2[I] : SHAPE == 1 ? hi1[I] : hi0[I];
 };
 
-template <int SHAPE>
-__device__ __forceinline__ void df_walk_all(const DecimFastArgs& A, const uint64_t*& p, uint32_t& cm, uint32_t rm, uint64_t (&acc)[kDfR])
+template <int SHAPE, int I>
+__device__ __forceinline__ void df_segment(const DecimFastArgs& A, uint32_t& p, int& u, uint32_t& ri, uint64_t (&acc)[kDfR])
 {
-    df_walk<DfRange<SHAPE, 0>::lo, DfRange<SHAPE, 0>::hi>(A, p, cm, rm, A.cuts[0], A.cuts[1], acc);
-    df_walk<DfRange<SHAPE, 1>::lo, DfRange<SHAPE, 1>::hi>(A, p, cm, rm, A.cuts[1], A.cuts[2], acc);
-    df_walk<DfRange<SHAPE, 2>::lo, DfRange<SHAPE, 2>::hi>(A, p, cm, rm, A.cuts[2], A.cuts[3], acc);
-    df_walk<DfRange<SHAPE, 3>::lo, DfRange<SHAPE, 3>::hi>(A, p, cm, rm, A.cuts[3], A.cuts[4], acc);
-    df_walk<DfRange<SHAPE, 4>::lo, DfRange<SHAPE, 4>::hi>(A, p, cm, rm, A.cuts[4], A.cuts[5], acc);
-    df_walk<DfRange<SHAPE, 5>::lo, DfRange<SHAPE, 5>::hi>(A, p, cm, rm, A.cuts[5], A.cuts[6], acc);
-    df_walk<DfRange<SHAPE, 6>::lo, DfRange<SHAPE, 6>::hi>(A, p, cm, rm, A.cuts[6], A.cuts[7], acc);
-}
-
-template <int IN>
-__device__ __forceinline__ void df_mix_group(const uint4& raw, const float2* tab, uint32_t ph, float2* dst)
-{
-    if constexpr (IN == I16) {
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-        for (int s = 0; s < 4; s++) dst[s] = cmul_unfused(ingest_i16(w[s]), __ldg(tab + ph + s));
-    } else {
-        dst[0] = cmul_unfused(make_float2(__uint_as_float(raw.x), __uint_as_float(raw.y)), __ldg(tab + ph));
-        dst[1] = cmul_unfused(make_float2(__uint_as_float(raw.z), __uint_as_float(raw.w)), __ldg(tab + ph + 1));
+    const uint32_t re = ri + A.nruns[I];
+    for (; ri < re; ri++) {
+        const DfRun r = A.runs[ri];
+        df_walk<DfRange<SHAPE, I>::lo, DfRange<SHAPE, I>::hi>(A, p, u, r.n, acc);
+        p -= 8u * r.skip;
     }
 }
 
-template <int IN, int OUT, int SHAPE>
-__global__ void __launch_bounds__(kDfThreads) mix_decimate_fast_kernel(const __grid_constant__ DecimFastArgs A)
+template <int SHAPE>
+__device__ __forceinline__ void df_walk_all(const DecimFastArgs& A, uint32_t p, uint64_t (&acc)[kDfR])
 {
-    constexpr int R = kDfR, NT = kDfThreads;
+    int u = 0;
+    uint32_t ri = 0;
+    df_segment<SHAPE, 0>(A, p, u, ri, acc);
+    df_segment<SHAPE, 1>(A, p, u, ri, acc);
+    df_segment<SHAPE, 2>(A, p, u, ri, acc);
+    df_segment<SHAPE, 3>(A, p, u, ri, acc);
+    df_segment<SHAPE, 4>(A, p, u, ri, acc);
+    df_segment<SHAPE, 5>(A, p, u, ri, acc);
+    df_segment<SHAPE, 6>(A, p, u, ri, acc);
+}
+
+// one 16-byte group (4 i16 or 2 f32 samples) against table entries ph, ph + 1, ...: mixed samples to shared address dst
+template <int IN, bool TAB_SMEM>
+__device__ __forceinline__ void df_mix_group(const uint4& raw, const float2* tab, uint32_t tab_addr, uint32_t ph, uint32_t dst)
+{
+    constexpr int V = IN == I16 ? 4 : 2;
+    float2 phs[V];
+#pragma unroll
+    for (int s = 0; s < V; s++) {
+        if constexpr (TAB_SMEM)
+            phs[s] = lds_f32x2(tab_addr + (ph + s) * 8u);
+        else
+            phs[s] = __ldg(tab + ph + s);
+    }
+    if constexpr (IN == I16) {
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int s = 0; s < 4; s++) sts_f32x2(dst + 8u * s, cmul_unfused(ingest_i16(w[s]), phs[s]));
+    } else {
+        sts_f32x2(dst, cmul_unfused(make_float2(__uint_as_float(raw.x), __uint_as_float(raw.y)), phs[0]));
+        sts_f32x2(dst + 8u, cmul_unfused(make_float2(__uint_as_float(raw.z), __uint_as_float(raw.w)), phs[1]));
+    }
+}
+
+// Phase A inside one tabled piece.  Group g of the step (16 bytes: 4 i16 or 2 f32 samples) belongs to thread g mod NT; a BATCH is
+// UNR groups per thread.  The loads of batch b + 1 are issued before batch b is mixed (two register buffers), and batch 0 of
+// the NEXT step before this step's walk (df_prefetch), so a CTA keeps global loads in flight through both of its phases.
+constexpr int kDfUnr = 4;
+
+template <int NT>
+__device__ __forceinline__ void df_load_batch(uint4 (&r)[kDfUnr], const unsigned char* src, uint32_t batch, uint32_t ngroups, uint32_t tid)
+{
+    const unsigned char* s = src + (size_t)batch * (kDfUnr * NT * 16);
+    const uint32_t g = batch * (kDfUnr * NT) + tid;
+#pragma unroll
+    for (int x = 0; x < kDfUnr; x++)
+        if (g + x * NT < ngroups) r[x] = __ldcs(reinterpret_cast<const uint4*>(s + x * NT * 16));
+}
+
+template <int IN, bool TAB_SMEM, int NT>
+__device__ __forceinline__ void df_stage_fast(const DecimFastArgs& A, const DevPiece& p, const unsigned char* src, int64_t ia, uint32_t ngroups,
+                                              uint32_t ys_addr, uint32_t tab_addr, uint32_t tid, uint4 (&bufA)[kDfUnr], uint4 (&bufB)[kDfUnr],
+                                              bool have_batch0)
+{
+    constexpr uint32_t V = IN == I16 ? 4 : 2;
+    constexpr int UNR = kDfUnr;
+    const float2* tab = A.d.mix.tables + p.tab;
+    const uint32_t period = p.period;
+    uint32_t ph = piece_samplenum(p, (uint32_t)ia + tid * V - p.k_begin) - 1u;   // table phase of this thread's next group
+    const uint32_t ph_step = (NT * V) % period;
+    uint32_t j = tid * V;                                                         // staged index of this thread's next group
+    auto mix_batch = [&](const uint4 (&r)[UNR], uint32_t batch) {
+        const uint32_t g = batch * (UNR * NT) + tid;
+#pragma unroll
+        for (int x = 0; x < UNR; x++) {
+            if (g + x * NT < ngroups) {
+                df_mix_group<IN, TAB_SMEM>(r[x], tab, tab_addr, ph, ys_addr + (j + __umulhi(j, A.rm_magic)) * 8u);
+                j += NT * V;
+                ph += ph_step;
+                if (ph >= period) ph -= period;
+            }
+        }
+    };
+    const uint32_t nb = (ngroups + UNR * NT - 1) / (UNR * NT);
+    if (!have_batch0) df_load_batch<NT>(bufA, src, 0, ngroups, tid);
+    for (uint32_t b = 0; b < nb; b += 2) {
+        if (b + 1 < nb) df_load_batch<NT>(bufB, src, b + 1, ngroups, tid);
+        mix_batch(bufA, b);
+        if (b + 1 < nb) {
+            if (b + 2 < nb) df_load_batch<NT>(bufA, src, b + 2, ngroups, tid);
+            mix_batch(bufB, b + 1);
+        }
+    }
+}
+
+template <int IN, int OUT, int SHAPE, int NT>
+__global__ void __launch_bounds__(NT) mix_decimate_fast_kernel(const __grid_constant__ DecimFastArgs A)
+{
+    constexpr int R = kDfR;
     constexpr uint32_t V = IN == I16 ? 4 : 2;             // samples per 16-byte load
     constexpr uint32_t kInBps = IN == I16 ? 4 : 8;
-    constexpr int UNR = 4;                                // loads in flight per thread
     extern __shared__ __align__(16) unsigned char smem[];
-    float2* y_s = reinterpret_cast<float2*>(smem);
+    const uint32_t tab_addr = smem_u32(smem);             // [phasor table: tab_cap entries][staged samples]
+    const uint32_t ys_addr = tab_addr + A.tab_cap * 8u;
+    float2* tab_s = reinterpret_cast<float2*>(smem);
+    float2* y_s = tab_s + A.tab_cap;
     const DecimArgs& d = A.d;
     const uint32_t M = d.M, RM = R * M, nh = d.ntaps - 1u, OT = A.tb * R, tid = threadIdx.x;
     const unsigned char* gin = static_cast<const unsigned char*>(d.mix.in);
     const uint32_t warp0 = __shfl_sync(0xffffffffu, tid & ~31u, 0);   // first thread of this warp, known uniform to the compiler
-    uint32_t pi = 0;
+    uint32_t pi = 0, tab_piece = kNoPiece;                             // tab_piece: the piece whose table is in shared memory
     DevPiece p = get_piece(d.mix, 0);
+    uint4 bufA[kDfUnr], bufB[kDfUnr];
+    bool have_batch0 = false;   // bufA holds batch 0 of the coming step (loaded before the previous step's walk)
+    // staged index j of a step holds call-relative sample ia + j (negative: history); ia is a multiple of 4
+    auto step_origin = [&](uint32_t ob) { return (int64_t)d.first_out + (int64_t)ob * M - (int64_t)nh - (int64_t)A.lead; };
+    auto step_groups = [&](uint32_t ob) {
+        const uint32_t oc = d.nout - ob < OT ? d.nout - ob : OT;
+        return (A.lead + (oc - 1u) * M + d.ntaps + V - 1u) / V;
+    };
+    auto in_input = [&](int64_t ia, uint32_t ngroups) { return ia >= 0 && (uint64_t)ia + (uint64_t)ngroups * V <= (uint64_t)d.mix.nsamples; };
     for (uint32_t ob = blockIdx.x * OT; ob < d.nout; ob += gridDim.x * OT) {
         const uint32_t ocount = d.nout - ob < OT ? d.nout - ob : OT;
-        // staged index j holds call-relative sample ia + j (negative: history); ia is a multiple of 4
-        const int64_t ia = (int64_t)d.first_out + (int64_t)ob * M - (int64_t)nh - (int64_t)A.lead;
+        const int64_t ia = step_origin(ob);
         const uint32_t count = A.lead + (ocount - 1u) * M + d.ntaps;
-        const uint32_t ngroups = (count + V - 1u) / V;
-        __syncthreads();   // the previous step's walks are done
+        const uint32_t ngroups = step_groups(ob);
         // ---- phase A: mix the step's samples into shared memory
         bool fast = false;
-        if (ia >= 0 && (uint64_t)ia + (uint64_t)ngroups * V <= (uint64_t)d.mix.nsamples) {
+        if (in_input(ia, ngroups)) {
             const uint32_t first = (uint32_t)ia, last = first + ngroups * V;
             if (first >= p.k_end || first < p.k_begin) {
                 pi = find_piece(d.mix, first < p.k_begin ? 0u : pi, first);
@@ -157,36 +273,19 @@ __global__ void __launch_bounds__(kDfThreads) mix_decimate_fast_kernel(const __g
             }
             fast = last <= p.k_end && p.tab != kNoTab;
         }
-        if (fast) {
+        const bool tab_smem = fast && p.period + (uint32_t)kTabPad <= A.tab_cap;
+        if (tab_smem && tab_piece != pi) {   // (block-uniform) first step inside this piece: copy its table
+            __syncthreads();                 // the previous table's readers are done
             const float2* tab = d.mix.tables + p.tab;
-            const uint32_t period = p.period;
-            // group g = tid + x * NT: sample ia + g * V, staged index j = g * V = jq * RM + jr, table phase ph
-            uint32_t ph = piece_samplenum(p, (uint32_t)ia + tid * V - p.k_begin) - 1u;
-            const uint32_t ph_step = (NT * V) % period;
-            uint32_t jq = (tid * V) / RM, jr = (tid * V) % RM;
-            const uint32_t jq_step = (NT * V) / RM, jr_step = (NT * V) % RM;
-            const unsigned char* src = gin + ((size_t)ia + (size_t)tid * V) * kInBps;
-            for (uint32_t g0 = tid; g0 < ngroups; g0 += UNR * NT) {
-                uint4 raw[UNR];
-#pragma unroll
-                for (int x = 0; x < UNR; x++)
-                    if (g0 + x * NT < ngroups) raw[x] = __ldcs(reinterpret_cast<const uint4*>(src + (size_t)x * NT * 16));
-                src += (size_t)UNR * NT * 16;
-#pragma unroll
-                for (int x = 0; x < UNR; x++) {
-                    if (g0 + x * NT < ngroups) {
-                        df_mix_group<IN>(raw[x], tab, ph, y_s + (jq * RM + jr) + jq);
-                        ph += ph_step;
-                        if (ph >= period) ph -= period;
-                        jq += jq_step;
-                        jr += jr_step;
-                        if (jr >= RM) {
-                            jr -= RM;
-                            jq++;
-                        }
-                    }
-                }
-            }
+            for (uint32_t e = tid; e < p.period + (uint32_t)kTabPad; e += NT) tab_s[e] = __ldg(tab + e);
+            tab_piece = pi;
+        }
+        __syncthreads();   // the previous step's walks are done (and the table is staged)
+        const unsigned char* src = gin + ((size_t)ia + (size_t)tid * V) * kInBps;   // (only dereferenced on the fast paths)
+        if (tab_smem) {
+            df_stage_fast<IN, true, NT>(A, p, src, ia, ngroups, ys_addr, tab_addr, tid, bufA, bufB, have_batch0);
+        } else if (fast) {
+            df_stage_fast<IN, false, NT>(A, p, src, ia, ngroups, ys_addr, tab_addr, tid, bufA, bufB, have_batch0);
         } else {
             for (uint32_t j = tid; j < count; j += NT) {
                 const int64_t i = ia + (int64_t)j;
@@ -199,6 +298,19 @@ __global__ void __launch_bounds__(kDfThreads) mix_decimate_fast_kernel(const __g
                 y_s[j + j / RM] = y;
             }
         }
+        // batch 0 of this CTA's next step goes out now: its latency hides behind the walk
+        have_batch0 = false;
+        {
+            const uint64_t ob_next = (uint64_t)ob + (uint64_t)gridDim.x * OT;
+            if (ob_next < d.nout) {
+                const int64_t ia_n = step_origin((uint32_t)ob_next);
+                const uint32_t ng_n = step_groups((uint32_t)ob_next);
+                if (in_input(ia_n, ng_n)) {
+                    df_load_batch<NT>(bufA, gin + ((size_t)ia_n + (size_t)tid * V) * kInBps, 0, ng_n, tid);
+                    have_batch0 = true;
+                }
+            }
+        }
         __syncthreads();
         // ---- phase B: thread tid owns outputs ob + 4 * tid + (0 .. 3)
         // (a warp-uniform condition: the walk's tap reads and loop control stay on the uniform datapath; lanes past the last
@@ -207,10 +319,7 @@ __global__ void __launch_bounds__(kDfThreads) mix_decimate_fast_kernel(const __g
             uint64_t acc[R];
 #pragma unroll
             for (int k = 0; k < R; k++) acc[k] = 0ull;   // (+0.0f, +0.0f)
-            const uint32_t c0 = A.ctop;
-            const uint64_t* yp = reinterpret_cast<const uint64_t*>(y_s) + tid * (RM + 1u) + c0 + c0 / RM;
-            uint32_t cm = c0 % RM;
-            df_walk_all<SHAPE>(A, yp, cm, RM, acc);
+            df_walk_all<SHAPE>(A, ys_addr + (tid * (RM + 1u) + A.slot0) * 8u, acc);
             const uint32_t m0 = tid * R;
             float2 z[R];
 #pragma unroll

@@ -136,6 +136,7 @@ struct doppler_b200_ctx {
     uint32_t small_max = kSmallMaxSamples;
     bool seg_alt = false;               // doppler_b200_tune: use StreamShape::seg_alt
     bool decim_generic = false;         // doppler_b200_tune: the fused decimator always takes the generic kernel
+    uint32_t decim_stage_slots = dmix::kDfStageSlots;   // doppler_b200_tune: shared-memory slots of one CTA step of the register-blocked decimator
     uint32_t max_claim = 1;             // work units claimed at once by the segmented kernels (doppler_b200_tune; chunks of up to 8
                                         // lost the A/B by 6-15 %, profiles/r02_ab_seg.jsonl)
     size_t tiny_host_bytes = kTinyHostBytes;
@@ -1176,6 +1177,9 @@ int doppler_b200_tune(doppler_b200_ctx* ctx, int knob, uint64_t value)
     case DOPPLER_B200_TUNE_DECIM_VARIANT:
         ctx->decim_generic = value != 0;
         return DOPPLER_B200_OK;
+    case DOPPLER_B200_TUNE_DECIM_STAGE_SLOTS:
+        ctx->decim_stage_slots = (uint32_t)std::max<uint64_t>(512, std::min<uint64_t>(value, 27000));
+        return DOPPLER_B200_OK;
     case DOPPLER_B200_TUNE_MAX_CLAIM:
         ctx->max_claim = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(value, 64));
         return DOPPLER_B200_OK;
@@ -1281,6 +1285,7 @@ struct doppler_b200_decim {
     bool hist_event_valid = false;
     // register-blocked kernel (decimate_kernels.cuh): tap layout and walk segments of this filter, or fast_ok == false
     bool fast_ok = false;
+    uint32_t cuts[8] = {};              // sorted bounds of the walk's segments
     dmix::DecimFastArgs fast;
 };
 
@@ -1292,8 +1297,8 @@ constexpr uint32_t kDecimStageSlots = 5120;   // mixed samples staged per CTA st
 using DecimKernel = void (*)(const dmix::DecimArgs);
 using DecimFastKernel = void (*)(const dmix::DecimFastArgs);
 
-// Register-blocked kernel: the filter's tap layout per walk position and the walk's segments (decimate_kernels.cuh).  The
-// envelope: the layout fits the kernel parameters, and at least one warp's worth of output-owning threads fits the stage.
+// Register-blocked kernel (decimate_kernels.cuh): what depends on the filter alone -- the tap layout per walk position, the
+// sorted segment bounds, the shape.  The envelope: the layout fits the kernel parameters.
 void decim_fast_setup(doppler_b200_decim* d, const float* taps)
 {
     constexpr uint32_t R = dmix::kDfR;
@@ -1302,30 +1307,65 @@ void decim_fast_setup(doppler_b200_decim* d, const float* taps)
     if (M > 64 || ntq > (uint32_t)dmix::kDfMaxTq) return;
     dmix::DecimFastArgs& f = d->fast;
     memset(&f, 0, sizeof f);
-    // a CTA step stages lead (<= 3) + (4 * tb - 1) * M + ntaps samples (+ one 16-byte group of slack), one padding slot per 4M
-    uint32_t tb = dmix::kDfThreads;
-    for (; tb >= 32; tb -= 32) {
-        const uint64_t count = 3 + (uint64_t)(R * tb - 1) * M + ntaps + 4;
-        if (count + count / (R * M) + 2 <= dmix::kDfStageSlots) break;
-    }
-    if (tb < 32) return;
-    f.tb = tb;
     for (uint32_t u = 0; u < ntq; u++)
         for (uint32_t k = 0; k < R; k++) {
             const int64_t t = (int64_t)u - (int64_t)(R - 1 - k) * M;
             const float h = (t >= 0 && t < (int64_t)ntaps) ? taps[t] : 0.0f;
             uint32_t b;
             memcpy(&b, &h, 4);
-            f.tq[u][k] = (uint64_t)b | ((uint64_t)b << 32);
+            f.tq[u].h[k] = (uint64_t)b | ((uint64_t)b << 32);
         }
     // output k is active at walk positions [(3 - k) * M, (3 - k) * M + ntaps): the sorted bounds cut the walk into 7 segments
     for (uint32_t k = 0; k < R; k++) {
-        f.cuts[k] = k * M;
-        f.cuts[R + k] = k * M + ntaps;
+        d->cuts[k] = k * M;
+        d->cuts[R + k] = k * M + ntaps;
     }
-    std::sort(f.cuts, f.cuts + 2 * R);
+    std::sort(d->cuts, d->cuts + 2 * R);
     f.shape = std::min<uint32_t>(3, (ntaps - 1) / M);
+    f.rm_magic = (uint32_t)((1ull << 32) / (R * M)) + 1u;
     d->fast_ok = true;
+}
+
+// ... and what depends on the call: threads per CTA from the stage budget, the staging origin, and the walk's runs (the segments
+// cut again where the walk crosses a padding slot).  False when the launch does not fit (the generic kernel takes it).
+bool decim_fast_plan(doppler_b200_decim* d, uint64_t i0, uint32_t stage_slots, const std::vector<DevPiece>& pieces, size_t* smem_bytes)
+{
+    constexpr uint32_t R = dmix::kDfR;
+    const uint32_t M = d->M, ntaps = d->ntaps, RM = R * M;
+    dmix::DecimFastArgs& f = d->fast;
+    f.lead = (uint32_t)((((int64_t)i0 - (int64_t)(ntaps - 1)) % 4 + 4) % 4);
+    // a CTA step stages lead + (4 * tb - 1) * M + ntaps samples (+ one 16-byte group of slack), one padding slot per 4M
+    uint32_t tb = dmix::kDfMaxThreads;
+    uint64_t slots = 0;
+    for (; tb >= 32; tb -= 32) {
+        const uint64_t count = f.lead + (uint64_t)(R * tb - 1) * M + ntaps + 4;
+        slots = count + count / RM + 2;
+        if (slots <= stage_slots) break;
+    }
+    if (tb < 32) return false;
+    f.tb = tb;
+    const uint32_t c0 = f.lead + (ntaps - 1) + (R - 1) * M;
+    f.slot0 = c0 + c0 / RM;
+    uint32_t ri = 0;
+    for (int i = 0; i < 7; i++) {
+        f.nruns[i] = 0;
+        for (uint32_t u = d->cuts[i]; u < d->cuts[i + 1];) {
+            const uint32_t cm = (c0 - u) % RM, left = d->cuts[i + 1] - u;   // cm more positions before the next padding slot
+            const bool cross = cm < left;
+            const uint32_t n = cross ? cm + 1 : left;
+            if (ri == (uint32_t)dmix::kDfMaxRuns) return false;
+            f.runs[ri++] = dmix::DfRun{(uint16_t)n, (uint16_t)(cross ? 1 : 0)};
+            f.nruns[i]++;
+            u += n;
+        }
+    }
+    // the longest tabled period that fits the CTA's table area decides its size
+    uint32_t cap = 0;
+    for (const DevPiece& p : pieces)
+        if (p.tab != dmix::kNoTab && p.period + dmix::kTabPad <= dmix::kDfTabCap) cap = std::max<uint32_t>(cap, p.period + dmix::kTabPad);
+    f.tab_cap = (cap + 1) & ~1u;
+    *smem_bytes = (size_t)f.tab_cap * sizeof(float2) + (size_t)slots * sizeof(float2);
+    return true;
 }
 
 // One device-resident call of the fused stage: `runs` over n samples at d_in; outputs to d_out.  Asynchronous on `s`.
@@ -1399,25 +1439,26 @@ int decimate_launch(doppler_b200_decim* dec, const void* d_in, uint64_t n, int i
     const size_t smem = ((dec->ntaps * 4 + 15) & ~(size_t)15) + slots * sizeof(float2);
     static const DecimKernel kern[2][2] = {{dmix::mix_decimate_kernel<0, 0>, dmix::mix_decimate_kernel<0, 1>},
                                            {dmix::mix_decimate_kernel<1, 0>, dmix::mix_decimate_kernel<1, 1>}};
-#define DF_SHAPES(I, O) {dmix::mix_decimate_fast_kernel<I, O, 0>, dmix::mix_decimate_fast_kernel<I, O, 1>, \
-                         dmix::mix_decimate_fast_kernel<I, O, 2>, dmix::mix_decimate_fast_kernel<I, O, 3>}
-    static const DecimFastKernel fkern[2][2][4] = {{DF_SHAPES(0, 0), DF_SHAPES(0, 1)}, {DF_SHAPES(1, 0), DF_SHAPES(1, 1)}};
+#define DF_SHAPES(I, O, NT) {dmix::mix_decimate_fast_kernel<I, O, 0, NT>, dmix::mix_decimate_fast_kernel<I, O, 1, NT>, \
+                             dmix::mix_decimate_fast_kernel<I, O, 2, NT>, dmix::mix_decimate_fast_kernel<I, O, 3, NT>}
+    // [CTA of 256 / 128 threads][intype][outtype][shape]
+    static const DecimFastKernel fkern[2][2][2][4] = {{{DF_SHAPES(0, 0, 256), DF_SHAPES(0, 1, 256)}, {DF_SHAPES(1, 0, 256), DF_SHAPES(1, 1, 256)}},
+                                                      {{DF_SHAPES(0, 0, 128), DF_SHAPES(0, 1, 128)}, {DF_SHAPES(1, 0, 128), DF_SHAPES(1, 1, 128)}}};
 #undef DF_SHAPES
-    if (nout && dec->fast_ok && !ctx->decim_generic && ((((uintptr_t)d_in) | ((uintptr_t)d_out)) & 15) == 0) {
+    size_t fsmem = 0;
+    if (nout && dec->fast_ok && !ctx->decim_generic && ((((uintptr_t)d_in) | ((uintptr_t)d_out)) & 15) == 0 &&
+        decim_fast_plan(dec, i0, ctx->decim_stage_slots, dev, &fsmem)) {
         // register-blocked kernel: 4 consecutive outputs per thread, taps in the kernel parameters (decimate_kernels.cuh)
         constexpr uint32_t R = dmix::kDfR;
         dmix::DecimFastArgs& f = dec->fast;
         f.d = a;
-        f.lead = (uint32_t)((((int64_t)i0 - (int64_t)(dec->ntaps - 1)) % 4 + 4) % 4);
-        f.ctop = f.lead + (dec->ntaps - 1) + (R - 1) * M;
-        const uint64_t count = f.lead + (uint64_t)(R * f.tb - 1) * M + dec->ntaps + 4;
-        const size_t fsmem = (size_t)(count + count / (R * M) + 2) * sizeof(float2);
         const uint64_t steps = (nout + (uint64_t)R * f.tb - 1) / ((uint64_t)R * f.tb);
-        const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(2048 / dmix::kDfThreads, (size_t)(227 * 1024) / (fsmem + 1024)));
+        const uint32_t nt = f.tb > 128 ? 256 : 128;   // CTA size: the next instantiated size that holds the output-owning threads
+        const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(2048 / nt, (size_t)(227 * 1024) / (fsmem + 1024)));
         const uint32_t grid = (uint32_t)std::min<uint64_t>(steps, (uint64_t)ctx->sm_count * per_sm);
-        const DecimFastKernel fk = fkern[intype][outtype][f.shape];
-        CUDA_TRY(ctx, cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dmix::kDfStageSlots * sizeof(float2))));
-        fk<<<grid, dmix::kDfThreads, fsmem, s>>>(f);
+        const DecimFastKernel fk = fkern[nt == 128][intype][outtype][f.shape];
+        CUDA_TRY(ctx, cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        fk<<<grid, nt, fsmem, s>>>(f);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
     } else if (nout) {

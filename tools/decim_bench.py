@@ -50,6 +50,8 @@ def main():
              (F32, I16, 10_000_000, 100000.0, 5, 41),
              (I16, I16, 256_000, -15000.0, 32, 128),
              (F32, I16, 1_024_000, -9876.54, 8, 49)]       # long period: no table, per-sample evaluation in phase A
+    if os.environ.get("DECIM_CASES"):                              # e.g. DECIM_CASES=0,1 (profiling one case under ncu)
+        cases = [cases[int(i)] for i in os.environ["DECIM_CASES"].split(",")]
     with open(out, "w") as f:
         for it, ot, fs, shift, M, ntaps in cases:
             taps = lowpass(ntaps, 0.4 / M)
