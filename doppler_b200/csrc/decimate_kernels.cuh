@@ -29,8 +29,17 @@
 // against a copy of the piece's phasor table in shared memory; phase B is the walk.  Several CTAs per SM overlap each other's
 // phases.  CTAs are 256 threads, or 128 where a stage of 256 * 4 outputs would not fit (M > 8).
 //
-// Launches outside the envelope (too many taps for the parameter block, M > 64, unaligned buffers) and pieces without a table
-// keep the generic paths: mix_decimate_kernel, or the per-sample loop of phase A below.
+// Launches outside the envelope (too many taps for the parameter block, M > 64, unaligned buffers, most samples in pieces
+// without a table -- long periods, track mode) keep the generic paths: mix_decimate_kernel, or the per-sample loop of phase A.
+//
+// Measured (B200, 256 M samples, tools/decim_bench.py, profiles/r02_decim_*): const f32 -> i16, M = 8, 49 taps 0.66-0.68 ms =
+// 380 Gsample/s in = 0.50 of the stage's HBM roofline (first version: 1.78 ms, 0.19); i16 -> i16 0.25 of its 4.5 B/sample
+// roofline.  ncu: 53 issued instructions per input sample at 57 % issue utilisation, load/store-unit wavefronts at 66 %
+// (two-thirds of them shared memory), 24 warps per SM -- the stage is bound by issue slots and the shared-memory pipe
+// together, not by HBM (39 % of peak).  Two restructurings that cut both counters but LOST on the clock, kept out of the tree:
+// two lockstep output groups per thread (tap loads and loop control shared by eight chains: 39 instructions per sample, but half
+// the warps per SM for the same shared memory: 0.75-0.80 ms) and one sample per lane in phase A (conflict-free shared memory,
+// same result).  Shared memory per resident warp is what limits the stage.
 #pragma once
 
 #include "mixer_kernels.cuh"
@@ -89,6 +98,14 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t addr)
 __device__ __forceinline__ void sts_f32x2(uint32_t addr, float2 v)
 {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+// the shared window's base as an opaque value (ptxas otherwise re-derives it from the cluster CTA id at every use: three issue
+// slots per staged group)
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v)
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
 }
 
 // n walk positions from u on, outputs KLO .. KHI active; p = shared address of this thread's slot of position u
@@ -239,7 +256,7 @@ __global__ void __launch_bounds__(NT) mix_decimate_fast_kernel(const __grid_cons
     constexpr uint32_t V = IN == I16 ? 4 : 2;             // samples per 16-byte load
     constexpr uint32_t kInBps = IN == I16 ? 4 : 8;
     extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t tab_addr = smem_u32(smem);             // [phasor table: tab_cap entries][staged samples]
+    const uint32_t tab_addr = opaque_u32(smem_u32(smem));   // [phasor table: tab_cap entries][staged samples]
     const uint32_t ys_addr = tab_addr + A.tab_cap * 8u;
     float2* tab_s = reinterpret_cast<float2*>(smem);
     float2* y_s = tab_s + A.tab_cap;
@@ -341,5 +358,12 @@ __global__ void __launch_bounds__(NT) mix_decimate_fast_kernel(const __grid_cons
         }
     }
 }
+
+using DecimFastKernel = void (*)(const DecimFastArgs);
+// one translation unit per type pair (decimate_inst.cu)
+DecimFastKernel df_kernel_0_0(int nt128, int shape);
+DecimFastKernel df_kernel_0_1(int nt128, int shape);
+DecimFastKernel df_kernel_1_0(int nt128, int shape);
+DecimFastKernel df_kernel_1_1(int nt128, int shape);
 
 }  // namespace dmix

@@ -1295,7 +1295,7 @@ constexpr uint32_t kDecimMaxTaps = 4096;
 constexpr uint32_t kDecimStageSlots = 5120;   // mixed samples staged per CTA step (40 KB)
 
 using DecimKernel = void (*)(const dmix::DecimArgs);
-using DecimFastKernel = void (*)(const dmix::DecimFastArgs);
+using dmix::DecimFastKernel;
 
 // Register-blocked kernel (decimate_kernels.cuh): what depends on the filter alone -- the tap layout per walk position, the
 // sorted segment bounds, the shape.  The envelope: the layout fits the kernel parameters.
@@ -1359,10 +1359,17 @@ bool decim_fast_plan(doppler_b200_decim* d, uint64_t i0, uint32_t stage_slots, c
             u += n;
         }
     }
-    // the longest tabled period that fits the CTA's table area decides its size
+    // the longest tabled period that fits the CTA's table area decides its size; a launch whose samples mostly lie in pieces
+    // WITHOUT a table (long periods, track mode) gains nothing from this kernel's staging loop and keeps the generic kernel
     uint32_t cap = 0;
-    for (const DevPiece& p : pieces)
-        if (p.tab != dmix::kNoTab && p.period + dmix::kTabPad <= dmix::kDfTabCap) cap = std::max<uint32_t>(cap, p.period + dmix::kTabPad);
+    uint64_t tabled = 0, total = 0;
+    for (const DevPiece& p : pieces) {
+        total += p.k_end - p.k_begin;
+        if (p.tab == dmix::kNoTab) continue;
+        tabled += p.k_end - p.k_begin;
+        if (p.period + dmix::kTabPad <= dmix::kDfTabCap) cap = std::max<uint32_t>(cap, p.period + dmix::kTabPad);
+    }
+    if (2 * tabled < total) return false;
     f.tab_cap = (cap + 1) & ~1u;
     *smem_bytes = (size_t)f.tab_cap * sizeof(float2) + (size_t)slots * sizeof(float2);
     return true;
@@ -1439,12 +1446,6 @@ int decimate_launch(doppler_b200_decim* dec, const void* d_in, uint64_t n, int i
     const size_t smem = ((dec->ntaps * 4 + 15) & ~(size_t)15) + slots * sizeof(float2);
     static const DecimKernel kern[2][2] = {{dmix::mix_decimate_kernel<0, 0>, dmix::mix_decimate_kernel<0, 1>},
                                            {dmix::mix_decimate_kernel<1, 0>, dmix::mix_decimate_kernel<1, 1>}};
-#define DF_SHAPES(I, O, NT) {dmix::mix_decimate_fast_kernel<I, O, 0, NT>, dmix::mix_decimate_fast_kernel<I, O, 1, NT>, \
-                             dmix::mix_decimate_fast_kernel<I, O, 2, NT>, dmix::mix_decimate_fast_kernel<I, O, 3, NT>}
-    // [CTA of 256 / 128 threads][intype][outtype][shape]
-    static const DecimFastKernel fkern[2][2][2][4] = {{{DF_SHAPES(0, 0, 256), DF_SHAPES(0, 1, 256)}, {DF_SHAPES(1, 0, 256), DF_SHAPES(1, 1, 256)}},
-                                                      {{DF_SHAPES(0, 0, 128), DF_SHAPES(0, 1, 128)}, {DF_SHAPES(1, 0, 128), DF_SHAPES(1, 1, 128)}}};
-#undef DF_SHAPES
     size_t fsmem = 0;
     if (nout && dec->fast_ok && !ctx->decim_generic && ((((uintptr_t)d_in) | ((uintptr_t)d_out)) & 15) == 0 &&
         decim_fast_plan(dec, i0, ctx->decim_stage_slots, dev, &fsmem)) {
@@ -1456,7 +1457,9 @@ int decimate_launch(doppler_b200_decim* dec, const void* d_in, uint64_t n, int i
         const uint32_t nt = f.tb > 128 ? 256 : 128;   // CTA size: the next instantiated size that holds the output-owning threads
         const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(2048 / nt, (size_t)(227 * 1024) / (fsmem + 1024)));
         const uint32_t grid = (uint32_t)std::min<uint64_t>(steps, (uint64_t)ctx->sm_count * per_sm);
-        const DecimFastKernel fk = fkern[nt == 128][intype][outtype][f.shape];
+        const DecimFastKernel fk = intype == DOPPLER_B200_I16
+                                       ? (outtype == DOPPLER_B200_I16 ? dmix::df_kernel_0_0 : dmix::df_kernel_0_1)(nt == 128, (int)f.shape)
+                                       : (outtype == DOPPLER_B200_I16 ? dmix::df_kernel_1_0 : dmix::df_kernel_1_1)(nt == 128, (int)f.shape);
         CUDA_TRY(ctx, cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         fk<<<grid, nt, fsmem, s>>>(f);
         CUDA_TRY(ctx, cudaGetLastError());

@@ -128,7 +128,7 @@ struct MixArgs {
 // Deliberately NOT inlined: this is the generic (any-range) routine of the rare paths -- tiles that
 // straddle pieces / ranges / period wraps, table builds, probes; the hot paths use tables or the
 // range-specialised rows below.  One shared copy keeps the kernels inside the instruction cache.
-__device__ __noinline__ float2 phasor(float r, uint32_t n)
+static __device__ __noinline__ float2 phasor(float r, uint32_t n)
 {
     const float x = __fmul_rn(r, __uint2float_rn(n));
     const float theta = __fmul_rn(__uint_as_float(0xC0C90FDBu) /* -2.0f * PI_f32 */, x);
@@ -1599,7 +1599,7 @@ __global__ void __launch_bounds__(kDecimThreads) decim_history_kernel(const __gr
 }
 
 // Phasor table of one shift: entry j (0 <= j < period + kTabPad) = phasor(r, (j mod period) + 1).
-__global__ void __launch_bounds__(kThreads) build_phasor_table_kernel(float2* tab, float r, uint32_t period, uint32_t entries)
+static __global__ void __launch_bounds__(kThreads) build_phasor_table_kernel(float2* tab, float r, uint32_t period, uint32_t entries)
 {
     const uint32_t j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= entries) return;
@@ -1616,7 +1616,7 @@ __global__ void __launch_bounds__(kThreads) convert_kernel(const void* in, float
 }
 
 // self-test probes (doppler_b200_phasor_probe / doppler_b200_sincosf_probe)
-__global__ void phasor_probe_kernel(float r, uint32_t n0, uint32_t count, float* c, float* s)
+static __global__ void phasor_probe_kernel(float r, uint32_t n0, uint32_t count, float* c, float* s)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -1625,7 +1625,7 @@ __global__ void phasor_probe_kernel(float r, uint32_t n0, uint32_t count, float*
     s[i] = ph.y;
 }
 
-__global__ void sincosf_probe_kernel(uint32_t first, uint32_t stride, uint32_t count, float* s, float* c)
+static __global__ void sincosf_probe_kernel(uint32_t first, uint32_t stride, uint32_t count, float* s, float* c)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;

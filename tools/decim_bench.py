@@ -64,12 +64,15 @@ def main():
             y = torch.empty((n // M + 2) * BPS[ot], dtype=torch.uint8, device=dev)
             w = 1 << 18
             want, _ = oracle.mix_decimate(x[:w * BPS[it]].cpu().numpy(), it, ot, shift, fs, taps, M)
-            res, ok = {"register-blocked": [], "generic": []}, {}
+            variants = [("register-blocked", 0, None), ("generic", 1, None)]
+            if os.environ.get("DECIM_SLOTS"):                      # stage-size sweep of the register-blocked kernel
+                variants = [(f"register-blocked slots={v}", 0, int(v)) for v in os.environ["DECIM_SLOTS"].split(",")]
+            res, ok = {v[0]: [] for v in variants}, {}
             for rep in range(3):
-                for name, variant in (("register-blocked", 0), ("generic", 1)):
+                for name, variant, slots in variants:
                     if name == "generic" and rep > 0 and n > 64_000_000:
                         continue                                   # the generic kernel is 4x slower: one repeat
-                    mixer.tune(decim_variant=variant)
+                    mixer.tune(decim_variant=variant, decim_stage_slots=slots)
                     dec.reset()
                     y.zero_()
                     torch.cuda.synchronize()
