@@ -502,7 +502,8 @@ def run_f4(mixer, stream, D, peak):
             "samples_per_gpu": n, "ms_per_call": med * 1e3, "msps_in": D.world * n / med / 1e6, "bytes_per_input_sample": bps,
             "frac": n * bps / med / 1e9 / peak, "parity_ok": D.all_true(ok), "parity_samples_checked": w,
             "e2e_msps_in": D.world * ne / statistics.median(tt) / 1e6, "e2e_d2h_bytes": 4 * (ne // M),
-            "note": "not in the reference (SURVEY 8f row 4); specification = oracle_mix_decimate; first correct version, not tuned to the roofline"}
+            "kernel": "dmix::mix_decimate_fast_kernel (4 consecutive outputs per thread, taps as uniform-register FFMA2 operands from the kernel parameters)",
+            "note": "not in the reference (SURVEY 8f row 4); specification = oracle_mix_decimate; bound by issue slots + the shared-memory pipe, not HBM (profiles/r02_ncu_decim_f32_i16.txt)"}
 
 
 def run_cfg1_cli(oracle_threads):

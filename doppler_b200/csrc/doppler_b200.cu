@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <memory>
@@ -145,6 +146,13 @@ struct doppler_b200_ctx {
     uint32_t* done_flag_dev = nullptr;  // its device alias
     uint32_t* done_counter = nullptr;   // device
     uint32_t done_token = 0;
+    // resident kernel of the per-block host path (mixer_kernels.cuh: mix_resident_kernel)
+    dmix::RtMailbox* rt_mb = nullptr;       // mapped pinned host memory
+    dmix::RtMailbox* rt_mb_dev = nullptr;   // its device alias
+    cudaStream_t rt_stream = nullptr;
+    uint32_t rt_seq = 0, rt_gen = 0;
+    uint64_t rt_idle_us = 20000;            // the kernel leaves after this long without a request; 0: no resident kernel (doppler_b200_tune)
+    uint64_t rt_requests = 0, rt_starts = 0;
     // DOPPLER_B200_TRACE=1: phase clock of the tiny host path (ns totals: staging in, plan + launch, wait for the flag, copy out)
     bool trace = false;
     uint64_t tiny_calls = 0, tiny_ns[4] = {0, 0, 0, 0};
@@ -274,6 +282,8 @@ void magic_for(uint32_t d, uint32_t* magic, uint32_t* shift)
 // kNoTab when a table is not worthwhile.  Only periods that fit the kernel's shared-memory table
 // get one; longer periods are mixed as COLUMN segments (phasors evaluated once per column and
 // reused over rows) or, with fewer than kColumnMinRows whole periods, evaluated per sample.
+void rt_quiesce(doppler_b200_ctx* ctx);   // the resident kernel of the per-block host path leaves (defined with it below)
+
 int get_table(doppler_b200_ctx* ctx, float r, uint32_t period, uint64_t piece_len, cudaStream_t s, uint32_t* off_out)
 {
     *off_out = dmix::kNoTab;
@@ -295,6 +305,7 @@ int get_table(doppler_b200_ctx* ctx, float r, uint32_t period, uint64_t piece_le
         // Recycle in place: the arena is a fixed block allocated once, so a stream that forms a new ratio per
         // block for hours (realtime track mode) never pays a free / malloc.  Launches that still read the old
         // tables are drained first -- one device-wide wait per >= 1000 table builds.
+        rt_quiesce(ctx);
         CUDA_TRY(ctx, cudaDeviceSynchronize());
         ctx->arena_used = 0;
         ctx->tables.clear();
@@ -515,8 +526,11 @@ SmallKernel small_kernel_for(int in, int out, bool wide)
 }
 
 // `done` (optional): have the last CTA of a small launch raise a flag in host memory (zero-copy per-block path).
+// `rt_args` (optional, with `done`): if the call is ONE small launch whose pieces fit the kernel arguments, do not launch:
+// hand the arguments back (*rt_filled = true) for the resident kernel's mailbox.
 int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t nsamples, int intype, int outtype,
-               const std::vector<dplan::Run>& runs, uint32_t* samplenum, cudaStream_t s, const dmix::SmallDone* done = nullptr)
+               const std::vector<dplan::Run>& runs, uint32_t* samplenum, cudaStream_t s, const dmix::SmallDone* done = nullptr,
+               MixArgs* rt_args = nullptr, bool* rt_filled = nullptr)
 {
     if (nsamples == 0) return DOPPLER_B200_OK;
     std::vector<dplan::Piece> pieces;
@@ -650,6 +664,12 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
                 a.seg_index = reinterpret_cast<const uint32_t*>(d_meta + off_index);
             }
         }
+        if (small && rt_args && !up_pieces && l0 == 0 && l1 == nsamples) {
+            *rt_args = a;
+            *rt_filled = true;
+            *samplenum = sn_after;
+            return DOPPLER_B200_OK;
+        }
         if (small) {
             // one group per thread while that still fills the chip once over (latency), kSmallV per thread beyond (bytes in
             // flight); a flagged zero-copy launch of up to 1024 groups is ONE CTA: no cross-CTA counter before the flag
@@ -702,6 +722,7 @@ int ensure_slot(doppler_b200_ctx* ctx, Slot& sl, size_t in_bytes, size_t out_byt
         CUDA_TRY(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     }
+    if (sl.in_cap < in_bytes || sl.out_cap < out_bytes) rt_quiesce(ctx);   // (freeing synchronises the device)
     if (sl.in_cap < in_bytes) {
         if (sl.d_in) cudaFree(sl.d_in);
         if (sl.h_in) cudaFreeHost(sl.h_in);
@@ -839,6 +860,79 @@ int device_alias(doppler_b200_ctx* ctx, const void* host, void** dev)
     return DOPPLER_B200_OK;
 }
 
+// ---- resident kernel (mixer_kernels.cuh: mix_resident_kernel) --------------------------------------------------------------
+int rt_start(doppler_b200_ctx* ctx)
+{
+    if (!ctx->rt_mb) {
+        CUDA_TRY(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->rt_mb), sizeof(dmix::RtMailbox), cudaHostAllocMapped));
+        memset(ctx->rt_mb, 0, sizeof(dmix::RtMailbox));
+        void* alias = nullptr;
+        CUDA_TRY(ctx, cudaHostGetDevicePointer(&alias, ctx->rt_mb, 0));
+        ctx->rt_mb_dev = static_cast<dmix::RtMailbox*>(alias);
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->rt_stream, cudaStreamNonBlocking));
+    }
+    const uint32_t gen = ++ctx->rt_gen ? ctx->rt_gen : ++ctx->rt_gen;   // never 0
+    ctx->rt_mb->alive = gen;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    // (queued behind a predecessor that is still leaving: same stream)
+    dmix::mix_resident_kernel<<<1, dmix::kSmallThreads, 0, ctx->rt_stream>>>(ctx->rt_mb_dev, ctx->rt_idle_us * 1000ull, gen);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    ctx->rt_starts++;
+    return DOPPLER_B200_OK;
+}
+
+// The resident kernel leaves now (before anything that synchronises the device, frees memory it may read, or ends the context).
+void rt_quiesce(doppler_b200_ctx* ctx)
+{
+    if (!ctx->rt_mb) return;
+    ctx->rt_mb->quit = 1;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    cudaStreamSynchronize(ctx->rt_stream);
+    ctx->rt_mb->quit = 0;
+    ctx->rt_mb->alive = 0;
+    cudaGetLastError();
+}
+
+// One request through the mailbox; returns when its output is visible in host memory.
+int rt_request(doppler_b200_ctx* ctx, const MixArgs& a, int intype, int outtype)
+{
+    dmix::RtMailbox* mb = ctx->rt_mb;
+    if (!mb || mb->alive == 0) {
+        int rc = rt_start(ctx);
+        if (rc) return rc;
+        mb = ctx->rt_mb;
+    }
+    // the request in tagged 64-byte lines: payload first, then the line's tag (mixer_kernels.cuh: RtMailbox)
+    uint32_t payload[dmix::kRtLines * 15] = {0};
+    payload[0] = (uint32_t)intype;
+    payload[1] = (uint32_t)outtype;
+    memcpy(payload + 2, &a, sizeof a);
+    const uint32_t seq = ++ctx->rt_seq ? ctx->rt_seq : ++ctx->rt_seq;   // (0 is the mailbox's initial state)
+    for (int l = 0; l < dmix::kRtLines; l++) {
+        volatile uint32_t* line = mb->req[l].w;
+        for (int i = 0; i < 15; i++) line[i] = payload[l * 15 + i];
+        std::atomic_thread_fence(std::memory_order_release);
+        *const_cast<volatile uint32_t*>(&mb->req[l].tag) = seq;
+    }
+    ctx->rt_requests++;
+    for (uint32_t spins = 1; mb->served != seq; spins++) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0x3fffu) == 0) {   // every ~100 us: did the kernel leave (idle time-out racing this request) or die?
+            const cudaError_t q = cudaStreamQuery(ctx->rt_stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return fail(ctx, DOPPLER_B200_ECUDA, "resident kernel failed: %s", cudaGetErrorString(q));
+            if (q == cudaSuccess && mb->served != seq) {
+                int rc = rt_start(ctx);
+                if (rc) return rc;
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return DOPPLER_B200_OK;
+}
+
 int tiny_host_call(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int intype, int outtype, const float* shifts,
                    size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint32_t* samplenum, void* out)
 {
@@ -886,8 +980,33 @@ int tiny_host_call(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int
         runs = dplan::runs_from_blocks(shifts, nblocks, block_samples, samplerate, nsamples);
     const uint32_t token = ++ctx->done_token ? ctx->done_token : ++ctx->done_token;   // never 0
     const dmix::SmallDone done{ctx->done_counter, ctx->done_flag_dev, token};
-    rc = launch_mix(ctx, src_dev, dst_dev, nsamples, intype, outtype, runs, samplenum, sl.stream, &done);
+    // staged blocks (the reference's 8192-byte pump block) go to the resident kernel when their plan fits its mailbox
+    MixArgs rt_args;
+    bool rt_filled = false;
+    const bool rt_try = ctx->rt_idle_us != 0 && !probe;
+    const uint64_t launches_before = ctx->launches;
+    rc = launch_mix(ctx, src_dev, dst_dev, nsamples, intype, outtype, runs, samplenum, sl.stream, &done, rt_try ? &rt_args : nullptr, &rt_filled);
     if (rc) return rc;
+    if (rt_filled) {
+        // a phasor table this block needs may have been enqueued just now, or earlier on another stream
+        if (ctx->launches != launches_before) CUDA_TRY(ctx, cudaStreamSynchronize(sl.stream));
+        if (ctx->tables_event_valid) {
+            CUDA_TRY(ctx, cudaEventSynchronize(ctx->tables_ready));
+            ctx->tables_event_valid = false;
+        }
+        const auto t_2r = std::chrono::steady_clock::now();
+        rc = rt_request(ctx, rt_args, intype, outtype);
+        if (rc) return rc;
+        const auto t_3r = std::chrono::steady_clock::now();
+        memcpy(out, dst, nsamples * obps);
+        if (ctx->trace) {
+            const auto t_4r = std::chrono::steady_clock::now();
+            auto ns = [](auto a, auto b) { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+            ctx->tiny_calls++;
+            ctx->tiny_ns[0] += ns(t_0, t_1), ctx->tiny_ns[1] += ns(t_1, t_2r), ctx->tiny_ns[2] += ns(t_2r, t_3r), ctx->tiny_ns[3] += ns(t_3r, t_4r);
+        }
+        return DOPPLER_B200_OK;
+    }
     const auto t_2 = std::chrono::steady_clock::now();
     // spin on the flag (host memory, written by the kernel's last CTA after a system-wide fence); a launch that died never
     // raises it, so the stream is consulted now and then
@@ -1072,6 +1191,7 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     ctx->trace = getenv("DOPPLER_B200_TRACE") != nullptr;
     if (const char* e = getenv("DOPPLER_B200_SMALL_MAX")) ctx->small_max = (uint32_t)strtoul(e, nullptr, 10);   // tuning knobs (tools/tune)
     if (const char* e = getenv("DOPPLER_B200_TINY_BYTES")) ctx->tiny_host_bytes = (size_t)strtoul(e, nullptr, 10);
+    if (const char* e = getenv("DOPPLER_B200_RESIDENT_IDLE_US")) ctx->rt_idle_us = strtoull(e, nullptr, 10);
     cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&ctx->meta_stream, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->tables_ready, cudaEventDisableTiming);
@@ -1094,7 +1214,10 @@ void doppler_b200_destroy(doppler_b200_ctx* ctx)
                 (unsigned long long)ctx->tiny_calls, (double)ctx->tiny_ns[0] / ctx->tiny_calls, (double)ctx->tiny_ns[1] / ctx->tiny_calls,
                 (double)ctx->tiny_ns[2] / ctx->tiny_calls, (double)ctx->tiny_ns[3] / ctx->tiny_calls);
     cudaSetDevice(ctx->device);
+    rt_quiesce(ctx);
     cudaDeviceSynchronize();
+    if (ctx->rt_stream) cudaStreamDestroy(ctx->rt_stream);
+    if (ctx->rt_mb) cudaFreeHost(ctx->rt_mb);
     for (Slot& sl : ctx->slots) {
         if (sl.d_in) cudaFree(sl.d_in);
         if (sl.d_out) cudaFree(sl.d_out);
@@ -1165,9 +1288,16 @@ int doppler_b200_tune(doppler_b200_ctx* ctx, int knob, uint64_t value)
     case DOPPLER_B200_TUNE_SMALL_MAX_SAMPLES:
         ctx->small_max = (uint32_t)std::min<uint64_t>(value, kLaunchMaxSamples);
         return DOPPLER_B200_OK;
+    case DOPPLER_B200_TUNE_RESIDENT_IDLE_US:
+        if (value > 10000000) return fail(ctx, DOPPLER_B200_EINVAL, "resident kernel idle time-out is limited to 10 s");
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        rt_quiesce(ctx);
+        ctx->rt_idle_us = value;
+        return DOPPLER_B200_OK;
     case DOPPLER_B200_TUNE_TINY_HOST_BYTES:
         if (value > (8u << 20)) return fail(ctx, DOPPLER_B200_EINVAL, "tiny host path is limited to 8 MiB");
         CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        rt_quiesce(ctx);
         abandon_slots(ctx);
         ctx->tiny_host_bytes = (size_t)value;
         return DOPPLER_B200_OK;
@@ -1608,6 +1738,7 @@ void doppler_b200_decim_destroy(doppler_b200_decim* d)
 {
     if (!d) return;
     cudaSetDevice(d->ctx->device);
+    rt_quiesce(d->ctx);
     cudaDeviceSynchronize();
     if (d->d_taps) cudaFree(d->d_taps);
     for (float2* h : d->d_hist)
@@ -1621,6 +1752,7 @@ int doppler_b200_decim_reset(doppler_b200_decim* d)
 {
     if (!d) return DOPPLER_B200_EINVAL;
     CUDA_TRY(d->ctx, cudaSetDevice(d->ctx->device));
+    rt_quiesce(d->ctx);
     CUDA_TRY(d->ctx, cudaDeviceSynchronize());
     const size_t hb = std::max<size_t>(d->ntaps - 1, 1) * sizeof(float2);
     for (float2* h : d->d_hist) CUDA_TRY(d->ctx, cudaMemset(h, 0, hb));

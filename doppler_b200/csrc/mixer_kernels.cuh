@@ -1410,8 +1410,12 @@ struct SmallDone {
 
 // V groups per thread per step, all V loads issued before the first is used (memory-level parallelism: the tiny
 // zero-copy launches are one CTA and pay a PCIe round trip per dependent load; the mid sizes want bytes in flight).
-template <int IN, int OUT, int V>
-__global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_constant__ MixArgs a, const SmallDone done)
+// CTA `cta` of `nctas` takes an equal, contiguous share of the groups.
+// COHERENT (the resident kernel below, which outlives many calls): input is read with ld.global.cv and tables with
+// ld.global.cg, so that neither a previous call's block in the same host buffer nor a neighbouring table built after the
+// kernel started can be served from this SM's L1.
+template <int IN, int OUT, int V, bool COHERENT>
+__device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint32_t nctas)
 {
     constexpr int G = group_samples(IN, OUT);
     constexpr uint32_t kStep = kSmallThreads * V;
@@ -1420,8 +1424,8 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
     DevPiece p = get_piece(a, 0);
     // every CTA takes an equal, contiguous share of the groups (a grid-stride loop over fixed steps leaves whole steps
     // unevenly spread: 2.06 steps per CTA means a third of the CTAs run 3 while the rest wait)
-    const uint32_t g_begin = (uint32_t)((uint64_t)ngroups * blockIdx.x / gridDim.x);
-    const uint32_t g_end = (uint32_t)((uint64_t)ngroups * (blockIdx.x + 1) / gridDim.x);
+    const uint32_t g_begin = (uint32_t)((uint64_t)ngroups * cta / nctas);
+    const uint32_t g_end = (uint32_t)((uint64_t)ngroups * (cta + 1) / nctas);
     for (uint32_t base = g_begin; base < g_end; base += kStep) {
         uint32_t w[V][4];
 #pragma unroll
@@ -1430,10 +1434,12 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
             w[v][0] = w[v][1] = w[v][2] = w[v][3] = 0;
             if (g < g_end) {
                 if constexpr (IN == I16 && G == 2) {
-                    const uint2 x = __ldcs(reinterpret_cast<const uint2*>(a.in) + g);
+                    const uint2* src = reinterpret_cast<const uint2*>(a.in) + g;
+                    const uint2 x = COHERENT ? __ldcv(src) : __ldcs(src);
                     w[v][0] = x.x, w[v][1] = x.y;
                 } else {
-                    const uint4 x = __ldcs(reinterpret_cast<const uint4*>(a.in) + g);
+                    const uint4* src = reinterpret_cast<const uint4*>(a.in) + g;
+                    const uint4 x = COHERENT ? __ldcv(src) : __ldcs(src);
                     w[v][0] = x.x, w[v][1] = x.y, w[v][2] = x.z, w[v][3] = x.w;
                 }
             }
@@ -1459,7 +1465,7 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
                 // inside one tabled piece: entries j .. j+G-1 of its table (replicated kTabPad >= G-1 entries past the period)
                 const float2* tab = a.tables + p.tab + (piece_samplenum(p, k0 - p.k_begin) - 1u);
 #pragma unroll
-                for (int i = 0; i < G; i++) res[i] = cmul_unfused(smp[i], __ldg(tab + i));
+                for (int i = 0; i < G; i++) res[i] = cmul_unfused(smp[i], COHERENT ? __ldcg(tab + i) : __ldg(tab + i));
             } else {
                 uint32_t qi = pi;
                 DevPiece q = p;
@@ -1483,12 +1489,27 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
         }
     }
     // ragged end (fewer samples than a group): one thread each
-    const uint32_t tail = ngroups * G + blockIdx.x * kSmallThreads + threadIdx.x;
+    const uint32_t tail = ngroups * G + cta * kSmallThreads + threadIdx.x;
     if (tail < a.nsamples) {
         const uint32_t qi = find_piece(a, 0, tail);
         const DevPiece q = get_piece(a, qi);
-        store_sample<OUT>(a.out, tail, cmul_unfused(load_sample<IN>(a.in, tail), phasor(q.r, piece_samplenum(q, tail - q.k_begin))));
+        float2 smp;
+        if constexpr (COHERENT) {
+            if constexpr (IN == I16)
+                smp = ingest_i16(__ldcv(reinterpret_cast<const uint32_t*>(a.in) + tail));
+            else
+                smp = __ldcv(reinterpret_cast<const float2*>(a.in) + tail);
+        } else {
+            smp = load_sample<IN>(a.in, tail);
+        }
+        store_sample<OUT>(a.out, tail, cmul_unfused(smp, phasor(q.r, piece_samplenum(q, tail - q.k_begin))));
     }
+}
+
+template <int IN, int OUT, int V>
+__global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_constant__ MixArgs a, const SmallDone done)
+{
+    small_body<IN, OUT, V, false>(a, blockIdx.x, gridDim.x);
     if (done.flag) {
         __threadfence_system();   // this thread's stores (possibly into host memory) are visible before the flag can be
         __syncthreads();
@@ -1501,6 +1522,108 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
                 *done.flag = done.token;
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resident kernel: the per-block host path without a launch per block.
+//
+// The reference calls its mixer once per 8192-byte pump block (main.rs:49,70), and a realtime stream delivers such a block
+// every few milliseconds.  Even the zero-copy small launch above spends most of its ~14 us in the launch itself (driver call,
+// launch latency, kernel start-up).  So the first per-block call starts ONE CTA that stays on the chip and serves the following
+// blocks from a mailbox in mapped pinned host memory:
+//     host:   copy the block into the pinned staging buffer, plan it, write request n (types + MixArgs) into the mailbox
+//     device: the CTA reads the mailbox in one wave per look; on a new request it mixes the block straight from / to host
+//             memory, fences system-wide and writes served = n
+//     host:   spins on served (its own memory), copies the result out
+// Two PCIe round trips (request, block) and one posted write per block instead of a kernel launch.  The kernel leaves by itself after
+// `idle_ns` without a request (alive = 0, after one last look at seq), and at once when the host sets quit; the host starts
+// another when it finds alive == 0.  Only launches whose pieces fit MixArgs::inl come here.
+// Mailbox layout.  Every round trip over PCIe costs ~2 us, so a request must be visible to the device in ONE read: the request
+// (types + MixArgs) travels in 64-byte lines whose last word is the request number.  A PCIe read returns a coherent snapshot of
+// a cache line, and the host writes a line's payload before its tag (x86 stores are ordered), so a line whose tag is n carries
+// request n; the CTA reads all lines in one wave and takes the request when every tag shows the same new number.
+constexpr int kRtPayloadWords = 2 + (int)(sizeof(MixArgs) / 4);   // intype, outtype, MixArgs
+constexpr int kRtLines = (kRtPayloadWords + 14) / 15;
+struct RtLine {
+    uint32_t w[15];
+    uint32_t tag;
+};
+struct RtMailbox {
+    RtLine req[kRtLines];       // host -> device
+    volatile uint32_t quit;     // host -> device: leave now                                           (its own cache line)
+    uint32_t pad0[15];
+    volatile uint32_t served;   // device -> host: latest request whose output is visible to the host   (its own cache line)
+    volatile uint32_t alive;    // generation of the resident kernel (the host writes it before the launch); the kernel clears it when it leaves
+    uint32_t pad1[14];
+};
+static_assert(sizeof(RtLine) == 64 && sizeof(MixArgs) % 4 == 0, "mailbox lines");
+static_assert((kRtLines + 1) * 16 <= kSmallThreads, "one mailbox word per thread");
+
+__device__ __forceinline__ uint64_t global_timer_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+static __global__ void __launch_bounds__(kSmallThreads, 1) mix_resident_kernel(RtMailbox* mb, uint64_t idle_ns, uint32_t gen)
+{
+    __shared__ __align__(16) uint32_t s_words[kRtLines * 15 + 2];   // the request's payload: intype, outtype, MixArgs
+    __shared__ uint32_t s_tag[kRtLines];
+    __shared__ uint32_t s_quit, s_idle;
+    const uint32_t tid = threadIdx.x;
+    const volatile uint32_t* words = reinterpret_cast<const volatile uint32_t*>(mb);
+    uint32_t last = mb->served;   // (the same value in every thread; written by the previous resident kernel or the host)
+    uint64_t t0 = global_timer_ns();
+    bool last_look = false;
+    for (;;) {
+        // one wave over the mailbox: thread t reads word t of the request lines, thread kRtLines*16 the quit word
+        if (tid < (uint32_t)kRtLines * 16u) {
+            const uint32_t v = words[tid];
+            if ((tid & 15u) == 15u)
+                s_tag[tid >> 4] = v;
+            else
+                s_words[(tid >> 4) * 15u + (tid & 15u)] = v;
+        } else if (tid == (uint32_t)kRtLines * 16u) {
+            s_quit = mb->quit;
+            s_idle = global_timer_ns() - t0 > idle_ns ? 1u : 0u;
+        }
+        __syncthreads();
+        const uint32_t seq = s_tag[0];
+        bool whole = true;
+#pragma unroll
+        for (int i = 1; i < kRtLines; i++) whole = whole && s_tag[i] == seq;
+        const bool fresh = whole && seq != last;
+        const bool quit = s_quit != 0, idle = s_idle != 0;
+        if (fresh) {
+            const MixArgs& sa = *reinterpret_cast<const MixArgs*>(s_words + 2);
+            switch ((s_words[0] << 1) | s_words[1]) {
+            case 0: small_body<I16, I16, 4, true>(sa, 0, 1); break;
+            case 1: small_body<I16, F32, 4, true>(sa, 0, 1); break;
+            case 2: small_body<F32, I16, 4, true>(sa, 0, 1); break;
+            default: small_body<F32, F32, 4, true>(sa, 0, 1); break;
+            }
+            __threadfence_system();   // this thread's stores into host memory are visible before `served` can be
+            __syncthreads();
+            if (tid == 0) mb->served = seq;
+            last = seq;
+            t0 = global_timer_ns();
+        }
+        if (last_look || quit) break;
+        if (!fresh && idle) {
+            // idle: announce the departure, then look once more -- a request that raced with the time-out is still served
+            if (tid == 0) {
+                if (mb->alive == gen) mb->alive = 0;
+                __threadfence_system();
+            }
+            last_look = true;
+        }
+        __syncthreads();   // s_words / s_tag are rewritten next round
+    }
+    if (tid == 0) {
+        if (mb->alive == gen) mb->alive = 0;   // (a successor the host has already announced keeps its own mark)
+        __threadfence_system();
     }
 }
 

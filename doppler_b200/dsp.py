@@ -66,8 +66,10 @@ class Mixer:
     def synchronize(self):
         self._check(self._lib.doppler_b200_synchronize(self._ctx))
 
-    def tune(self, small_max_samples=None, tiny_host_bytes=None, seg_variant=None, max_claim=None, decim_variant=None, decim_stage_slots=None):
+    def tune(self, small_max_samples=None, tiny_host_bytes=None, seg_variant=None, max_claim=None, decim_variant=None, decim_stage_slots=None, resident_idle_us=None):
         """Thresholds between code paths (doppler_b200_tune); results are identical on every path."""
+        if resident_idle_us is not None:
+            self._check(self._lib.doppler_b200_tune(self._ctx, 7, int(resident_idle_us)))
         if decim_stage_slots is not None:
             self._check(self._lib.doppler_b200_tune(self._ctx, 6, int(decim_stage_slots)))
         if decim_variant is not None:

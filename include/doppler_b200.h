@@ -106,6 +106,9 @@ uint64_t doppler_b200_launch_count(const doppler_b200_ctx* ctx);
 #define DOPPLER_B200_TUNE_SEG_VARIANT 3 /* 0: the product's segmented kernels; 1: the experimental 4-warp pipelines where they exist (i16 -> i16) */
 #define DOPPLER_B200_TUNE_DECIM_VARIANT 5 /* 0: the fused decimator's register-blocked kernel where the filter fits it; 1: always the generic kernel */
 #define DOPPLER_B200_TUNE_DECIM_STAGE_SLOTS 6 /* 8-byte shared-memory slots one CTA step of the register-blocked decimator stages (512 .. 27000) */
+#define DOPPLER_B200_TUNE_RESIDENT_IDLE_US 7 /* per-block host calls (up to 32 KiB) are served by a resident one-CTA kernel through a mailbox in pinned host
+                                             * memory instead of a launch per block; the kernel leaves after this many microseconds without a request
+                                             * (default 20000; 0 = no resident kernel, every block is a launch) */
 int doppler_b200_tune(doppler_b200_ctx* ctx, int knob, uint64_t value);
 
 /* ---- the reference's inner boundary, one to one (host buffers) --------------------------- */

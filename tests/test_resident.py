@@ -1,0 +1,113 @@
+"""The resident kernel of the per-block host path (mixer_kernels.cuh: mix_resident_kernel; include/doppler_b200.h:
+DOPPLER_B200_TUNE_RESIDENT_IDLE_US).  The reference calls its mixer once per 8192-byte block (main.rs:49,70); here such calls are
+served by one CTA that stays on the chip and takes its requests from a mailbox in pinned host memory.  Results must not depend on
+which path served a block, the kernel must leave when idle and come back on demand, and nothing may hang when the context ends."""
+import time
+
+import numpy as np
+import pytest
+
+import doppler_b200
+from doppler_b200 import F32, I16
+from tests.oracle_lib import BUFFER_SIZE, same_bits_f32
+
+BPS = {I16: 4, F32: 8}
+pytestmark = pytest.mark.gpu
+
+
+def make_input(rng, n, typ):
+    if typ == I16:
+        return rng.integers(-32768, 32768, 2 * n, dtype=np.int32).astype("<i2").view(np.uint8)
+    return rng.uniform(-0.7, 0.7, 2 * n).astype("<f4").view(np.uint8)
+
+
+def same(got, want, outtype):
+    return np.array_equal(got, want) if outtype == I16 else same_bits_f32(got, want)
+
+
+@pytest.fixture
+def fresh():
+    m = doppler_b200.Mixer(0)
+    yield m
+    m.close()
+
+
+@pytest.mark.parametrize("intype,outtype", [(I16, I16), (I16, F32), (F32, I16), (F32, F32)])
+def test_block_stream_is_served_without_a_launch_per_block(oracle, fresh, intype, outtype):
+    """300 pump blocks with a new shift every few blocks (track mode's call pattern), samplenum carried: bytes equal to the
+    oracle's chain, and the library launched a handful of kernels (the resident one, a table or two), not one per block."""
+    rng = np.random.default_rng(11 + 2 * intype + outtype)
+    fs, bs = 1_024_000, BUFFER_SIZE // BPS[intype]
+    shifts = np.repeat(rng.uniform(-12000, 12000, 60).astype(np.float32), 5)
+    sn_g = sn_o = 0
+    before = fresh.launch_count
+    for b, shift in enumerate(shifts):
+        n = bs if b % 7 else int(rng.integers(1, bs))        # ragged blocks in between
+        buf = make_input(rng, n, intype)
+        got, sn_g = fresh.mix(buf, intype, outtype, float(shift), fs, samplenum=sn_g)
+        want, sn_o = oracle.mix(buf, intype, outtype, float(shift), fs, samplenum=sn_o)
+        assert sn_g == sn_o and same(got, want, outtype), b
+    assert fresh.launch_count - before <= 8
+
+
+def test_const_mode_blocks_with_a_phasor_table(oracle, fresh):
+    """Short period (P = 256): the blocks read a phasor table built by an ordinary launch on another stream."""
+    rng = np.random.default_rng(5)
+    sn_g = sn_o = 0
+    for b in range(50):
+        buf = make_input(rng, 2048, I16)
+        got, sn_g = fresh.mix(buf, I16, I16, -15000.0, 256000, samplenum=sn_g)
+        want, sn_o = oracle.mix(buf, I16, I16, -15000.0, 256000, samplenum=sn_o)
+        assert sn_g == sn_o and np.array_equal(got, want), b
+
+
+def test_kernel_leaves_when_idle_and_returns_on_demand(oracle, fresh):
+    fresh.tune(resident_idle_us=2000)
+    rng = np.random.default_rng(6)
+    buf = make_input(rng, 2048, I16)
+    want, _ = oracle.mix(buf, I16, F32, 7321.7, 1_024_000)
+    starts = []
+    for pause in (0.0, 0.0, 0.05, 0.0, 0.05, 0.004, 0.0):    # longer and shorter than the time-out
+        time.sleep(pause)
+        before = fresh.launch_count
+        got, _ = fresh.mix(buf, I16, F32, 7321.7, 1_024_000)
+        assert same_bits_f32(got, want)
+        starts.append(fresh.launch_count - before)
+    assert starts[0] >= 1 and starts[1] == 0                 # started by the first block, reused by the second
+    assert starts[2] >= 1 and starts[4] >= 1                 # gone after 50 ms of silence: a new one
+    assert sum(starts) <= 6
+
+
+def test_paths_agree_and_interleave(oracle, fresh):
+    """Resident kernel, one zero-copy launch per block, staged pipeline and a large call in between: same bytes."""
+    rng = np.random.default_rng(8)
+    small = make_input(rng, 1024, F32)
+    big = make_input(rng, 3_000_001, F32)
+    want_s, _ = oracle.mix(small, F32, I16, 100000.0, 10_000_000, samplenum=17)
+    want_b, _ = oracle.mix(big, F32, I16, 100000.0, 10_000_000)
+    for idle in (20000, 0, 20000):
+        fresh.tune(resident_idle_us=idle)
+        got, _ = fresh.mix(small, F32, I16, 100000.0, 10_000_000, samplenum=17)
+        assert np.array_equal(got, want_s)
+        got, _ = fresh.mix(big, F32, I16, 100000.0, 10_000_000)
+        assert np.array_equal(got, want_b)
+        got, _ = fresh.mix(small, F32, I16, 100000.0, 10_000_000, samplenum=17)
+        assert np.array_equal(got, want_s)
+    fresh.tune(tiny_host_bytes=0)
+    got, _ = fresh.mix(small, F32, I16, 100000.0, 10_000_000, samplenum=17)
+    assert np.array_equal(got, want_s)
+
+
+def test_context_ends_while_the_kernel_is_resident(oracle):
+    """destroy() right after a block: the kernel is told to leave, nothing waits for the idle time-out."""
+    rng = np.random.default_rng(9)
+    buf = make_input(rng, 2048, I16)
+    want, _ = oracle.mix(buf, I16, I16, 5000.0, 1_024_000)
+    for _ in range(3):
+        m = doppler_b200.Mixer(0)
+        m.tune(resident_idle_us=5_000_000)
+        got, _ = m.mix(buf, I16, I16, 5000.0, 1_024_000)
+        assert np.array_equal(got, want)
+        t0 = time.perf_counter()
+        m.close()
+        assert time.perf_counter() - t0 < 1.0

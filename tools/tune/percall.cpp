@@ -1,6 +1,6 @@
 // tools/tune/percall.cpp -- latency of the host-buffer C-ABI calls at the reference's own granularity
 // (one 8192-byte block per call, src/main.rs:49,70) and at the batched sizes INTEGRATION.md recommends,
-// with the zero-copy tiny path on (default) and off, pageable and pinned caller buffers.
+// with the resident kernel (default), with a zero-copy launch per block, and with the staged pipeline; pageable and pinned caller buffers.
 // Build: make -C tools/tune percall      Run (GPU box): tools/tune/percall
 #include <chrono>
 #include <cstdio>
@@ -19,11 +19,14 @@ int main()
     }
     auto now = [] { return std::chrono::steady_clock::now(); };
     const size_t sizes[] = {1024, 2048, 16384, 262144, 4194304, 33554432};   // complex samples per call
-    for (int tiny = 1; tiny >= 0; tiny--) {
+    for (int mode = 2; mode >= 0; mode--) {   // 2: resident kernel (blocks up to 32 KiB), 1: one zero-copy launch per block, 0: staged pipeline
+        const int tiny = mode >= 1;
         doppler_b200_tune(ctx, DOPPLER_B200_TUNE_TINY_HOST_BYTES, tiny ? (128u << 10) : 0);
+        doppler_b200_tune(ctx, DOPPLER_B200_TUNE_RESIDENT_IDLE_US, mode == 2 ? 20000 : 0);
         for (int pinned = 0; pinned < 2; pinned++)
             for (size_t n : sizes) {
                 if (pinned && n > 262144) continue;
+                if (mode == 1 && n > 8192) continue;   // (identical to mode 2 above 32 KiB)
                 const size_t bytes = n * 4;   // i16 IQ in and out
                 void *in, *out;
                 if (pinned) {
@@ -42,8 +45,9 @@ int main()
                 for (int i = 0; i < iters; i++)
                     if (doppler_b200_mix(ctx, in, bytes, DOPPLER_B200_I16, DOPPLER_B200_I16, 5000.0f, 1024000, &sn, out, bytes, &got) != 0) return 3;
                 const double us = std::chrono::duration<double, std::micro>(now() - t0).count() / iters;
-                printf("{\"call\": \"doppler_b200_mix i16->i16\", \"zero_copy_tiny_path\": %s, \"caller_buffers\": \"%s\", \"samples_per_call\": %zu, "
-                       "\"us_per_call\": %.2f, \"msps\": %.1f}\n", tiny ? "true" : "false", pinned ? "pinned" : "pageable", n, us, n / us);
+                printf("{\"call\": \"doppler_b200_mix i16->i16\", \"path\": \"%s\", \"caller_buffers\": \"%s\", \"samples_per_call\": %zu, "
+                       "\"us_per_call\": %.2f, \"msps\": %.1f}\n",
+                       mode == 2 ? "resident kernel / zero-copy" : mode == 1 ? "zero-copy launch per block" : "staged pipeline", pinned ? "pinned" : "pageable", n, us, n / us);
                 fflush(stdout);
                 if (pinned) {
                     doppler_b200_host_free(in);
