@@ -506,6 +506,23 @@ def run_f4(mixer, stream, D, peak):
             "note": "not in the reference (SURVEY 8f row 4); specification = oracle_mix_decimate; bound by issue slots + the shared-memory pipe, not HBM (profiles/r02_ncu_decim_f32_i16.txt)"}
 
 
+def run_per_block():
+    """The reference's own call granularity: one 8192-byte block (2048 i16 samples) per host call (main.rs:49,70), pageable
+    caller buffers, measured by the C harness tools/tune/percall (no Python in the loop): resident kernel (default) against one
+    zero-copy launch per block."""
+    exe = os.path.join(ROOT, "tools", "tune", "percall")
+    if not os.path.exists(exe):
+        return {"error": "tools/tune/percall is not built (python -c 'import __graft_entry__ as g; g.build()')"}
+    r = subprocess.run([exe], env=dict(os.environ, PERCALL_QUICK="1"), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=120)
+    rows = [json.loads(line) for line in r.stdout.splitlines() if line.startswith("{")]
+    out = {"workload": "doppler_b200_mix i16->i16, 2048 samples (8192 bytes) per call, shift 5000 Hz @ 1.024 Msps, pageable buffers, 5000 calls",
+           "reference_cpu_us_per_block": "~80 (25 Msample/s on one core, cpu_baseline.value_1core)"}
+    for row in rows:
+        key = "resident_kernel" if row["path"].startswith("resident") else "launch_per_block"
+        out[key] = {"us_per_call": row["us_per_call"], "msps": row["msps"]}
+    return out
+
+
 def run_cfg1_cli(oracle_threads):
     """cfg1: `doppler const -s 256000 -i i16 --shift -15000` over 1 s of i16 IQ through the CLI (stdin -> stdout), bytes
     compared with the oracle's restatement of the reference's const driver.  Wall clock of the whole process (CUDA
@@ -742,6 +759,12 @@ def main():
         configs["gpu_seconds"] = time.time() - t_c
 
     mixer.close()
+    if configs is not None and rank == 0 and world == 1:   # (its own process and context: after this one's is gone)
+        try:
+            configs["per_block_host_call"] = run_per_block()
+        except Exception as e:   # noqa: BLE001
+            configs["per_block_host_call"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     base = None
     if rank == 0:
         threads = host_threads()

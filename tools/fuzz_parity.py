@@ -4,8 +4,9 @@
 Random per-block schedules (shifts with short, long and no reset periods, |r| > 1, tiny r), random lengths
 from a few samples to ~12 M (so that GRID, COLUMN and slow tiles, the 4 Mi-sample COLUMN threshold and
 several host-pipeline chunks all occur), random start samplenum, all four type pairs.  Each trial runs on one of
-four code paths: the product's thresholds (small kernel / zero-copy path for short inputs), the bulk-async kernels
-only, a two-context device group (time slices with analytic seeds), and the fused mix + decimating FIR.
+five code paths: the product's thresholds (small kernel / zero-copy path for short inputs), the bulk-async kernels
+only, a two-context device group (time slices with analytic seeds), the fused mix + decimating FIR, and one call per
+8192-byte block (the resident kernel).
 Exits non-zero at the first mismatch and prints the reproducer."""
 import argparse
 import os
@@ -49,7 +50,11 @@ def main():
             buf = rng.integers(-32768, 32768, 2 * n, dtype=np.int32).astype(np.int16).view(np.uint8)
         else:
             buf = rng.uniform(-1.2, 1.2, 2 * n).astype(np.float32).view(np.uint8)
-        path = ("default", "bulk", "group", "decimate")[(t // 4) % 4]
+        path = ("default", "bulk", "group", "decimate", "perblock")[(t // 4) % 5]
+        if path == "perblock":                                   # the reference's call pattern: one call per 8192-byte block
+            shifts = shifts[:200]
+            buf = buf[:shifts.size * BUFFER_SIZE]
+            n = buf.size // BPS[intype]
         if path == "decimate":
             M, ntaps = int(rng.integers(1, 12)), int(rng.integers(1, 70))
             taps = rng.uniform(-0.3, 0.3, ntaps).astype(np.float32)
@@ -62,6 +67,13 @@ def main():
             dec.close()
             want, st = oracle.mix_decimate(buf, intype, outtype, shifts, fs, taps, M, {"samplenum": start, "hist": np.zeros(2 * max(ntaps - 1, 1), dtype=np.float32), "pos": 0})
             sn_ref = st["samplenum"]
+        elif path == "perblock":
+            parts, sn = [], start
+            for b in range(0, buf.size, BUFFER_SIZE):            # (served by the resident kernel after the first block)
+                g, sn = mixer.mix(buf[b:b + BUFFER_SIZE], intype, outtype, float(shifts[b // BUFFER_SIZE]), fs, samplenum=sn)
+                parts.append(g)
+            got = np.concatenate(parts)
+            want, sn_ref = oracle.mix_blocks_threads(buf, intype, outtype, shifts, fs, samplenum=start)
         else:
             m = {"default": mixer, "bulk": bulk, "group": group}[path]
             got, sn = m.mix_blocks(buf, intype, outtype, shifts, fs, samplenum=start)

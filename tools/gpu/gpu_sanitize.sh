@@ -66,6 +66,34 @@ for n in (5, 70_001, 200_003):
     bad += not ok
     print("decimate", n, "ok" if ok else "MISMATCH")
 d.close()
+# the register-blocked decimator (tabled shifts), both CTA sizes, and the generic kernel on the same filter
+for it, ot, shift, fs, M, ntaps in [(F32, I16, 100000.0, 10_000_000, 8, 49), (I16, F32, -15000.0, 256000, 4, 33), (F32, F32, -15000.0, 256000, 5, 12)]:
+    t = np.arange(ntaps) - (ntaps - 1) / 2.0
+    h = np.sinc(2 * 0.4 / M * t) * np.hamming(ntaps)
+    taps = (h / h.sum()).astype(np.float32)
+    for variant in (0, 1):
+        m.tune(decim_variant=variant)
+        d = doppler_b200.Decimator(m, taps, M)
+        st, sn = None, 0
+        for n in (7, 70_001, 150_003):
+            buf = (rng.integers(-32768, 32768, 2 * n, dtype=np.int32).astype(np.int16) if it == I16 else rng.uniform(-0.7, 0.7, 2 * n).astype(np.float32)).view(np.uint8)
+            got, sn = d.mix(buf, it, ot, shift, fs, samplenum=sn)
+            want, st = o.mix_decimate(buf, it, ot, shift, fs, taps, M, st)
+            ok = sn == st["samplenum"] and np.array_equal(got, want)
+            bad += not ok
+            print("decimate", "generic" if variant else "register-blocked", M, ntaps, n, "ok" if ok else "MISMATCH")
+        d.close()
+m.tune(decim_variant=0)
+# the resident kernel: a stream of pump blocks with changing shifts, then the context ends while it is resident
+sn = sn_ref = 0
+for b in range(40):
+    buf = rng.integers(-32768, 32768, 2 * 2048, dtype=np.int32).astype(np.int16).view(np.uint8)
+    shift = float(rng.uniform(-12000, 12000))
+    got, sn = m.mix(buf, I16, I16, shift, 1_024_000, samplenum=sn)
+    want, sn_ref = o.mix(buf, I16, I16, shift, 1_024_000, samplenum=sn_ref)
+    ok = sn == sn_ref and np.array_equal(got, want)
+    bad += not ok
+print("resident", "ok" if not bad else "MISMATCH")
 m.close()
 sys.exit(1 if bad else 0)
 PY

@@ -18,12 +18,13 @@ int main()
         return 2;
     }
     auto now = [] { return std::chrono::steady_clock::now(); };
-    const size_t sizes[] = {1024, 2048, 16384, 262144, 4194304, 33554432};   // complex samples per call
-    for (int mode = 2; mode >= 0; mode--) {   // 2: resident kernel (blocks up to 32 KiB), 1: one zero-copy launch per block, 0: staged pipeline
+    const bool quick = getenv("PERCALL_QUICK") != nullptr;   // bench.py: the 8192-byte block only, resident kernel vs launch per block
+    const std::vector<size_t> sizes = quick ? std::vector<size_t>{2048} : std::vector<size_t>{1024, 2048, 16384, 262144, 4194304, 33554432};   // complex samples per call
+    for (int mode = 2; mode >= (quick ? 1 : 0); mode--) {   // 2: resident kernel (blocks up to 32 KiB), 1: one zero-copy launch per block, 0: staged pipeline
         const int tiny = mode >= 1;
         doppler_b200_tune(ctx, DOPPLER_B200_TUNE_TINY_HOST_BYTES, tiny ? (128u << 10) : 0);
         doppler_b200_tune(ctx, DOPPLER_B200_TUNE_RESIDENT_IDLE_US, mode == 2 ? 20000 : 0);
-        for (int pinned = 0; pinned < 2; pinned++)
+        for (int pinned = 0; pinned < (quick ? 1 : 2); pinned++)
             for (size_t n : sizes) {
                 if (pinned && n > 262144) continue;
                 if (mode == 1 && n > 8192) continue;   // (identical to mode 2 above 32 KiB)
