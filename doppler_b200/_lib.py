@@ -104,6 +104,8 @@ SIGNATURES = {
     "doppler_b200_plan_tiles_trace": (ctypes.c_long, [ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
                                                       ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32,
                                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "doppler_b200_decim_walk_trace": (ctypes.c_long, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p,
+                                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "doppler_b200_pipeline_probe": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                    ctypes.c_size_t]),
     "doppler_b200_phasor_probe": (ctypes.c_int, [c_ctx, ctypes.c_float, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_void_p,

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(NT) mix_decimate_fast_kernel(const __grid_cons
     constexpr int R = kDfR;
     constexpr uint32_t V = IN == I16 ? 4 : 2;             // samples per 16-byte load
     constexpr uint32_t kInBps = IN == I16 ? 4 : 8;
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t tab_addr = opaque_u32(smem_u32(smem));   // [phasor table: tab_cap entries][staged samples]
     const uint32_t ys_addr = tab_addr + A.tab_cap * 8u;
     float2* tab_s = reinterpret_cast<float2*>(smem);

@@ -869,7 +869,10 @@ int rt_start(doppler_b200_ctx* ctx)
         void* alias = nullptr;
         CUDA_TRY(ctx, cudaHostGetDevicePointer(&alias, ctx->rt_mb, 0));
         ctx->rt_mb_dev = static_cast<dmix::RtMailbox*>(alias);
-        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->rt_stream, cudaStreamNonBlocking));
+        // highest priority: when the chip is full of another stream's CTAs, the one resident CTA is placed first
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->rt_stream, cudaStreamNonBlocking, prio_hi));
     }
     const uint32_t gen = ++ctx->rt_gen ? ctx->rt_gen : ++ctx->rt_gen;   // never 0
     ctx->rt_mb->alive = gen;
@@ -1763,6 +1766,68 @@ int doppler_b200_decim_reset(doppler_b200_decim* d)
 }
 
 uint64_t doppler_b200_decim_position(const doppler_b200_decim* d) { return d ? d->pos : 0; }
+
+long doppler_b200_decim_walk_trace(const float* taps, uint32_t ntaps, uint32_t decimation, uint64_t first_out, uint32_t* records,
+                                   uint32_t* tap_bits, size_t cap, uint32_t* info)
+{
+    if (!taps || ntaps == 0 || ntaps > kDecimMaxTaps || decimation == 0 || !records) return -1;
+    std::unique_ptr<doppler_b200_decim> d(new (std::nothrow) doppler_b200_decim);
+    if (!d) return -1;
+    d->ntaps = ntaps;
+    d->M = decimation;
+    decim_fast_setup(d.get(), taps);
+    size_t smem = 0;
+    uint32_t nt = 0;
+    // (a launch of tabled pieces only: one piece of period 100 covering the call)
+    std::vector<DevPiece> pieces(1);
+    memset(&pieces[0], 0, sizeof(DevPiece));
+    pieces[0].k_end = 1u << 20;
+    pieces[0].period = 100;
+    pieces[0].tab = 0;
+    if (!d->fast_ok || !decim_fast_plan(d.get(), first_out % decimation, dmix::kDfStageSlots, pieces, &smem)) return 0;
+    nt = d->fast.tb > 128 ? 256 : 128;
+    const dmix::DecimFastArgs& f = d->fast;
+    constexpr uint32_t R = dmix::kDfR;
+    const uint32_t M = decimation, RM = R * M;
+    static const int lo[4][7] = {{3, 1, 2, 1, 1, 1, 0}, {3, 2, 2, 1, 1, 0, 0}, {3, 2, 1, 1, 0, 0, 0}, {3, 2, 1, 0, 0, 0, 0}};
+    static const int hi[4][7] = {{3, 0, 2, 0, 1, 0, 0}, {3, 3, 2, 2, 1, 1, 0}, {3, 3, 3, 2, 2, 1, 0}, {3, 3, 3, 3, 2, 1, 0}};
+    // the device's ranges (decimate_kernels.cuh: DfRange) are the source of truth: the tables above must agree with them
+    static_assert(dmix::DfRange<3, 3>::lo == 0 && dmix::DfRange<3, 3>::hi == 3 && dmix::DfRange<0, 1>::lo == 1 && dmix::DfRange<0, 1>::hi == 0 &&
+                      dmix::DfRange<1, 2>::lo == 2 && dmix::DfRange<1, 2>::hi == 2 && dmix::DfRange<2, 3>::lo == 1 && dmix::DfRange<2, 3>::hi == 2,
+                  "walk ranges");
+    const uint32_t c0 = f.lead + (ntaps - 1) + (R - 1) * M;
+    int64_t slot = (int64_t)f.slot0;   // relative to the thread's base slot tid * (4M + 1)
+    uint32_t u = 0, ri = 0;
+    size_t n = 0;
+    for (int i = 0; i < 7; i++) {
+        for (uint32_t r = 0; r < f.nruns[i]; r++, ri++) {
+            for (uint32_t x = 0; x < f.runs[ri].n; x++, u++, slot--) {
+                if (n < cap) {
+                    uint32_t* rec = records + n * 8;
+                    rec[0] = c0 - u;
+                    rec[1] = (uint32_t)slot;
+                    rec[2] = (uint32_t)lo[f.shape][i];
+                    rec[3] = (uint32_t)hi[f.shape][i];
+                    for (uint32_t k = 0; k < R; k++) {
+                        const bool on = (int)k >= lo[f.shape][i] && (int)k <= hi[f.shape][i];
+                        rec[4 + k] = on ? u - (R - 1 - k) * M : 0xffffffffu;
+                        if (tap_bits) tap_bits[n * 4 + k] = (uint32_t)f.tq[u].h[k];
+                    }
+                }
+                n++;
+            }
+            slot -= f.runs[ri].skip;
+        }
+    }
+    (void)RM;
+    if (info) {
+        info[0] = f.tb;
+        info[1] = f.lead;
+        info[2] = nt;
+        info[3] = f.shape;
+    }
+    return (long)n;
+}
 
 int doppler_b200_mix_blocks_decimate(doppler_b200_decim* dec, const void* in, size_t in_len, int intype, int outtype,
                                      const float* shift_hz_per_block, size_t nblocks, size_t block_bytes, uint32_t samplerate,

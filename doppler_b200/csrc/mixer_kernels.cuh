@@ -1665,7 +1665,7 @@ __device__ __forceinline__ float2 mix_one(const MixArgs& a, uint32_t i, uint32_t
 template <int IN, int OUT>
 __global__ void __launch_bounds__(kDecimThreads) mix_decimate_kernel(const __grid_constant__ DecimArgs d)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     float* taps_s = reinterpret_cast<float*>(smem);
     float2* y_s = reinterpret_cast<float2*>(smem + ((d.ntaps * 4 + 15) & ~15u));
     const uint32_t nh = d.ntaps - 1u, M = d.M, OT = d.out_per_cta;

@@ -322,6 +322,17 @@ long doppler_b200_plan_tiles_trace(int intype, int outtype, uint32_t samplenum, 
                                    size_t nblocks, uint64_t block_samples, uint32_t samplerate, uint64_t count,
                                    uint32_t npipes, uint32_t* trace, uint32_t* cover, uint64_t* stats);
 
+/* Test/introspection hook (host only, no device needed): the register-blocked decimator's walk for a filter of `ntaps` taps
+ * and decimation M, for a call whose first output sits at call-relative sample `first_out` -- the same tap layout, segment
+ * bounds and run list the sm_100a kernel is launched with, replayed on the host.  One record per walk position u (at most
+ * `cap` records, 8 words each): { staged index relative to the thread's base, shared-memory slot relative to the thread's
+ * base slot, lowest active output klo, highest active output khi (klo > khi: none), tap index of output 0 .. 3 (0xffffffff
+ * where that output is inactive) }; tap_bits[u * 4 + k] (optional, cap * 4 words) = bit pattern of the tap the kernel multiplies
+ * for output k at position u.  info (optional, 4 words): threads per CTA that own outputs, staging lead, CTA size, shape.
+ * Returns the number of walk positions, 0 when the filter is outside the kernel's envelope, -1 on bad arguments. */
+long doppler_b200_decim_walk_trace(const float* taps, uint32_t ntaps, uint32_t decimation, uint64_t first_out, uint32_t* records,
+                                   uint32_t* tap_bits, size_t cap, uint32_t* info);
+
 /* Measurement hook: the host-buffer pipeline of doppler_b200_mix (same chunks, slots, streams, staging rules)
  * with the kernel SKIPPED: every chunk goes host -> device (in_len bytes) and the same number of samples'
  * worth of `outtype` bytes comes device -> host (content unspecified).  Its rate is the ceiling the box's

@@ -144,3 +144,61 @@ def test_mix_decimate_dev_and_argument_checks(oracle, mixer, decim_variant):
         doppler_b200.Decimator(mixer, np.zeros(0, dtype=np.float32), 4)
     with pytest.raises(doppler_b200.DopplerError):
         doppler_b200.Decimator(mixer, taps, 0)
+
+
+# ---- CPU: the register-blocked kernel's walk plan (host logic, no device) -----------------------------------------
+
+def walk_trace(taps, M, first_out=0):
+    import ctypes
+
+    from doppler_b200 import _lib
+    lib = _lib.load()
+    h = np.ascontiguousarray(taps, dtype=np.float32)
+    cap = 4 * M + h.size + 8
+    rec = np.zeros((cap, 8), dtype=np.uint32)
+    bits = np.zeros((cap, 4), dtype=np.uint32)
+    info = np.zeros(4, dtype=np.uint32)
+    n = lib.doppler_b200_decim_walk_trace(h.ctypes.data_as(ctypes.c_void_p), h.size, M, first_out, rec.ctypes.data_as(ctypes.c_void_p),
+                                          bits.ctypes.data_as(ctypes.c_void_p), cap, info.ctypes.data_as(ctypes.c_void_p))
+    return n, rec[:max(n, 0)], bits[:max(n, 0)], info
+
+
+@pytest.mark.parametrize("M,ntaps", FILTERS + [(3, 1), (1, 1), (64, 1), (2, 218), (12, 13), (12, 24), (12, 25), (12, 36), (12, 37)])
+@pytest.mark.parametrize("first_out", [0, 1, 5])
+def test_walk_plan_is_the_fir_in_tap_order(M, ntaps, first_out):
+    """The walk the kernel is launched with (tap layout in the kernel parameters, segment bounds, run list with the padding
+    slots) replayed on the host: every output of a thread's group must meet taps 0 .. ntaps-1 in that order, each with the
+    sample the specification pairs it with, at the shared-memory slot the staging phase wrote that sample to."""
+    rng = np.random.default_rng(ntaps * 131 + M)
+    taps = rng.uniform(-1, 1, ntaps).astype(np.float32)
+    n, rec, bits, info = walk_trace(taps, M, first_out % M)
+    if M > 64 or 3 * M + ntaps > 224:
+        assert n == 0                                             # outside the envelope: the generic kernel takes the launch
+        return
+    assert n == 3 * M + ntaps
+    tb, lead, nt, shape = (int(v) for v in info)
+    assert shape == min(3, (ntaps - 1) // M) and 32 <= tb <= nt and tb % 32 == 0 and nt in (128, 256)
+    assert lead == (first_out % M - (ntaps - 1)) % 4              # the staging origin is a multiple of 4 samples
+    RM = 4 * M
+    c0 = lead + (ntaps - 1) + 3 * M
+    seen = {k: [] for k in range(4)}
+    for u in range(n):
+        c, slot, klo, khi = (int(v) for v in rec[u, :4])
+        assert c == c0 - u and slot == c + c // RM                # newest first; one padding slot per 4M staged samples
+        for k in range(4):
+            t = int(rec[u, 4 + k])
+            active = klo <= k <= khi
+            assert active == (0 <= u - (3 - k) * M < ntaps)
+            if active:
+                assert t == u - (3 - k) * M
+                # output k of the group sits at staged index lead + (ntaps-1) + k*M; tap t pairs it with the sample t before
+                assert c == lead + (ntaps - 1) + k * M - t
+                assert bits[u, k] == taps[t:t + 1].view(np.uint32)[0]
+                seen[k].append(t)
+            else:
+                assert t == 0xffffffff
+    for k in range(4):
+        assert seen[k] == list(range(ntaps))                      # the specification's summation order
+    # the CTA's staged slots fit the shared-memory budget and threads' strides are odd in 8-byte units (conflict-free)
+    count = lead + (4 * tb - 1) * M + ntaps
+    assert count + count // RM + 2 <= 8448 and (RM + 1) % 2 == 1
