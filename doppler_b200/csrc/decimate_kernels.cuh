@@ -76,12 +76,6 @@ struct DecimFastArgs {
     DfTaps tq[kDfMaxTq];
 };
 
-__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c)
-{
-    uint64_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
 // 32-bit shared-window addresses: no generic-to-shared conversion inside the loops
 __device__ __forceinline__ uint64_t lds_u64(uint32_t addr)
 {
@@ -191,10 +185,10 @@ __device__ __forceinline__ void df_mix_group(const uint4& raw, const float2* tab
     if constexpr (IN == I16) {
         const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-        for (int s = 0; s < 4; s++) sts_f32x2(dst + 8u * s, cmul_unfused(ingest_i16(w[s]), phs[s]));
+        for (int s = 0; s < 4; s++) sts_f32x2(dst + 8u * s, cmul_unfused_fma(ingest_i16(w[s]), phs[s]));
     } else {
-        sts_f32x2(dst, cmul_unfused(make_float2(__uint_as_float(raw.x), __uint_as_float(raw.y)), phs[0]));
-        sts_f32x2(dst + 8u, cmul_unfused(make_float2(__uint_as_float(raw.z), __uint_as_float(raw.w)), phs[1]));
+        sts_f32x2(dst, cmul_unfused_fma(make_float2(__uint_as_float(raw.x), __uint_as_float(raw.y)), phs[0]));
+        sts_f32x2(dst + 8u, cmul_unfused_fma(make_float2(__uint_as_float(raw.z), __uint_as_float(raw.w)), phs[1]));
     }
 }
 

@@ -156,6 +156,15 @@ __device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b)
     return r;
 }
 
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// (1.0f, 1.0f), read from constant memory so that ptxas cannot see its value (below)
+static __constant__ unsigned long long kOnesF32x2 = 0x3f8000003f800000ull;
+
 // sample * corrector, num-complex 0.1.35 Mul: (a*c - b*d, a*d + b*c), four products and two
 // sums, each rounded separately (rustc never fuses).  The products are formed pairwise,
 // [a*c, b*c] and [b*(-d), a*d]; b*(-d) == -(b*d) and x + (-y) == x - y exactly in IEEE-754.
@@ -165,6 +174,26 @@ __device__ __forceinline__ float2 cmul_unfused(float2 smp, float2 ph)
     unpack_f32x2(mul_f32x2(pack_f32x2(smp.x, smp.y), pack_f32x2(ph.x, ph.x)), ac, bc);
     unpack_f32x2(mul_f32x2(pack_f32x2(smp.y, smp.x), pack_f32x2(-ph.y, ph.y)), nbd, ad);
     return make_float2(__fadd_rn(ac, nbd), __fadd_rn(ad, bc));
+}
+
+// The same product with the two sums as ONE packed instruction: fma(x, 1, y) rounds x * 1 + y == x + y once, exactly like the
+// add.  It has to be an fma by a multiplier ptxas cannot see through (constant memory): add.rn.f32x2 -- and an fma by a literal
+// 1.0 alike -- gets contracted with the preceding mul.rn.f32x2 into one FFMA2 even under --fmad=false, which drops the
+// product's rounding.  Three issue slots per complex multiply instead of four.  Measured (profiles/r02_ab_cmul.md, same
+// session, interleaved): it helps where instruction issue binds -- direct evaluation i16->i16 0.877 -> 0.901 of peak -- and
+// costs 0.5-1.7 % where HBM binds (the packed FFMA2 shares the pipe of the FMUL2s, the scalar FADDs do not), so only the
+// direct-evaluation rows and the fused decimator use it.
+__device__ __forceinline__ float2 cmul_unfused_fma(float2 smp, float2 ph)
+{
+#ifdef DOPPLER_CMUL_TWO_FADD   // A/B build (make variant_cmul): two scalar adds everywhere
+    return cmul_unfused(smp, ph);
+#else
+    const uint64_t acbc = mul_f32x2(pack_f32x2(smp.x, smp.y), pack_f32x2(ph.x, ph.x));
+    const uint64_t nbdad = mul_f32x2(pack_f32x2(smp.y, smp.x), pack_f32x2(-ph.y, ph.y));
+    float2 r;
+    unpack_f32x2(fma_f32x2(nbdad, kOnesF32x2, acbc), r.x, r.y);
+    return r;
+#endif
 }
 
 // i16 -> f32 of the low / high half of an IQ word without the slow-pipe I2F.S16 (measured ~4.5 issue cycles per warp
@@ -516,7 +545,7 @@ __device__ __forceinline__ void stream_rows(const uint32_t (&raw)[C::U][4], unsi
         float2 smp[G], res[G];
         unpack_group<IN, OUT, G>(raw[u], smp);
 #pragma unroll
-        for (int s = 0; s < G; s++) res[s] = cmul_unfused(smp[s], ph(u * C::kRow + s));
+        for (int s = 0; s < G; s++) res[s] = cmul_unfused_fma(smp[s], ph(u * C::kRow + s));
         stage_group<C, IN, OUT>(out_s, u, lane, res);
     }
 }
