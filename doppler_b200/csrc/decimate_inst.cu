@@ -1,4 +1,4 @@
-// decimate_inst.cu -- the instantiations of mix_decimate_fast_kernel for ONE type pair (-DDF_IN=.. -DDF_OUT=..): four
+// decimate_inst.cu -- the instantiations of mix_decimate_fast_kernel for ONE type pair (-DDF_IN=0|1|2 -DDF_OUT=0|1; 2 = already mixed): six
 // translation units built in parallel (the 32 instantiations in one unit took three minutes of nvcc).
 #include "decimate_kernels.cuh"
 

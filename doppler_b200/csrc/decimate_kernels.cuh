@@ -29,8 +29,12 @@
 // against a copy of the piece's phasor table in shared memory; phase B is the walk.  Several CTAs per SM overlap each other's
 // phases.  CTAs are 256 threads, or 128 where a stage of 256 * 4 outputs would not fit (M > 8).
 //
-// Launches outside the envelope (too many taps for the parameter block, M > 64, unaligned buffers, most samples in pieces
-// without a table -- long periods, track mode) keep the generic paths: mix_decimate_kernel, or the per-sample loop of phase A.
+// Launches whose samples mostly lie in pieces WITHOUT a table (long periods, track mode) run in TWO passes: the mixer itself
+// (mix_stream_kernel: COLUMN segments, range-specialised direct evaluation -- everything section 4.3/4.4 of DESIGN.md built for
+// such pieces) writes the mixed stream as complex f32 behind the carried history in a scratch buffer, and this kernel runs
+// over that buffer with input type C32 -- phase A is then a plain copy.  16 more bytes of HBM traffic per sample, but 2x faster
+// than evaluating one generic sincosf per sample here.  Launches outside the envelope (too many taps for the parameter block,
+// M > 64, unaligned buffers) keep the generic kernel, mix_decimate_kernel.
 //
 // Measured (B200, 256 M samples, tools/decim_bench.py, profiles/r02_decim_*): const f32 -> i16, M = 8, 49 taps 0.66-0.68 ms =
 // 380 Gsample/s in = 0.50 of the stage's HBM roofline (first version: 1.78 ms, 0.19); i16 -> i16 0.25 of its 4.5 B/sample
@@ -46,6 +50,7 @@
 
 namespace dmix {
 
+constexpr int C32 = 2;                  // a third "input type" of this kernel: samples that are already mixed (complex f32), see below
 constexpr int kDfR = 4;                 // outputs per thread
 constexpr int kDfMaxThreads = 256;
 constexpr int kDfMaxTq = 224;           // walk positions (3M + ntaps) the parameter block holds
@@ -173,6 +178,11 @@ __device__ __forceinline__ void df_walk_all(const DecimFastArgs& A, uint32_t p, 
 template <int IN, bool TAB_SMEM>
 __device__ __forceinline__ void df_mix_group(const uint4& raw, const float2* tab, uint32_t tab_addr, uint32_t ph, uint32_t dst)
 {
+    if constexpr (IN == C32) {   // already mixed: staged as they are
+        sts_f32x2(dst, make_float2(__uint_as_float(raw.x), __uint_as_float(raw.y)));
+        sts_f32x2(dst + 8u, make_float2(__uint_as_float(raw.z), __uint_as_float(raw.w)));
+        return;
+    }
     constexpr int V = IN == I16 ? 4 : 2;
     float2 phs[V];
 #pragma unroll
@@ -214,10 +224,10 @@ __device__ __forceinline__ void df_stage_fast(const DecimFastArgs& A, const DevP
 {
     constexpr uint32_t V = IN == I16 ? 4 : 2;
     constexpr int UNR = kDfUnr;
-    const float2* tab = A.d.mix.tables + p.tab;
-    const uint32_t period = p.period;
-    uint32_t ph = piece_samplenum(p, (uint32_t)ia + tid * V - p.k_begin) - 1u;   // table phase of this thread's next group
-    const uint32_t ph_step = (NT * V) % period;
+    const float2* tab = IN == C32 ? nullptr : A.d.mix.tables + p.tab;
+    const uint32_t period = IN == C32 ? 1u : p.period;
+    uint32_t ph = IN == C32 ? 0u : piece_samplenum(p, (uint32_t)ia + tid * V - p.k_begin) - 1u;   // table phase of this thread's next group
+    const uint32_t ph_step = IN == C32 ? 0u : (NT * V) % period;
     uint32_t j = tid * V;                                                         // staged index of this thread's next group
     auto mix_batch = [&](const uint4 (&r)[UNR], uint32_t batch) {
         const uint32_t g = batch * (UNR * NT) + tid;
@@ -226,8 +236,10 @@ __device__ __forceinline__ void df_stage_fast(const DecimFastArgs& A, const DevP
             if (g + x * NT < ngroups) {
                 df_mix_group<IN, TAB_SMEM>(r[x], tab, tab_addr, ph, ys_addr + (j + __umulhi(j, A.rm_magic)) * 8u);
                 j += NT * V;
-                ph += ph_step;
-                if (ph >= period) ph -= period;
+                if constexpr (IN != C32) {
+                    ph += ph_step;
+                    if (ph >= period) ph -= period;
+                }
             }
         }
     };
@@ -276,7 +288,9 @@ __global__ void __launch_bounds__(NT) mix_decimate_fast_kernel(const __grid_cons
         const uint32_t ngroups = step_groups(ob);
         // ---- phase A: mix the step's samples into shared memory
         bool fast = false;
-        if (in_input(ia, ngroups)) {
+        if constexpr (IN == C32) {
+            fast = in_input(ia, ngroups);   // no pieces, no table: the mixer has been here already
+        } else if (in_input(ia, ngroups)) {
             const uint32_t first = (uint32_t)ia, last = first + ngroups * V;
             if (first >= p.k_end || first < p.k_begin) {
                 pi = find_piece(d.mix, first < p.k_begin ? 0u : pi, first);
@@ -302,9 +316,12 @@ __global__ void __launch_bounds__(NT) mix_decimate_fast_kernel(const __grid_cons
                 const int64_t i = ia + (int64_t)j;
                 float2 y = make_float2(0.0f, 0.0f);   // before the history / past the input: never read by a valid output
                 if (i < 0) {
-                    if (i + (int64_t)nh >= 0) y = d.hist[(int64_t)nh + i];
+                    if (IN != C32 && i + (int64_t)nh >= 0) y = d.hist[(int64_t)nh + i];   // (C32: the history is part of the buffer)
                 } else if (i < (int64_t)d.mix.nsamples) {
-                    y = mix_one<IN>(d.mix, (uint32_t)i, pi, p);
+                    if constexpr (IN == C32)
+                        y = __ldcs(reinterpret_cast<const float2*>(gin) + i);
+                    else
+                        y = mix_one<IN>(d.mix, (uint32_t)i, pi, p);
                 }
                 y_s[j + j / RM] = y;
             }
@@ -359,5 +376,7 @@ DecimFastKernel df_kernel_0_0(int nt128, int shape);
 DecimFastKernel df_kernel_0_1(int nt128, int shape);
 DecimFastKernel df_kernel_1_0(int nt128, int shape);
 DecimFastKernel df_kernel_1_1(int nt128, int shape);
+DecimFastKernel df_kernel_2_0(int nt128, int shape);   // already-mixed input (two-pass form), i16 / f32 output
+DecimFastKernel df_kernel_2_1(int nt128, int shape);
 
 }  // namespace dmix

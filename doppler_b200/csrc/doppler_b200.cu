@@ -1418,6 +1418,12 @@ struct doppler_b200_decim {
     bool hist_event_valid = false;
     // register-blocked kernel (decimate_kernels.cuh): tap layout and walk segments of this filter, or fast_ok == false
     bool fast_ok = false;
+    struct Scratch {                    // two-pass form: the mixed stream of one call (history in front), one buffer per stream in use
+        cudaStream_t stream;
+        float2* buf;
+        size_t cap;                     // samples
+    };
+    std::vector<Scratch> scratch;
     uint32_t cuts[8] = {};              // sorted bounds of the walk's segments
     dmix::DecimFastArgs fast;
 };
@@ -1461,7 +1467,8 @@ void decim_fast_setup(doppler_b200_decim* d, const float* taps)
 
 // ... and what depends on the call: threads per CTA from the stage budget, the staging origin, and the walk's runs (the segments
 // cut again where the walk crosses a padding slot).  False when the launch does not fit (the generic kernel takes it).
-bool decim_fast_plan(doppler_b200_decim* d, uint64_t i0, uint32_t stage_slots, const std::vector<DevPiece>& pieces, size_t* smem_bytes)
+bool decim_fast_plan(doppler_b200_decim* d, uint64_t i0, uint32_t stage_slots, const std::vector<DevPiece>& pieces, size_t* smem_bytes,
+                     bool mixed = false)
 {
     constexpr uint32_t R = dmix::kDfR;
     const uint32_t M = d->M, ntaps = d->ntaps, RM = R * M;
@@ -1502,10 +1509,41 @@ bool decim_fast_plan(doppler_b200_decim* d, uint64_t i0, uint32_t stage_slots, c
         tabled += p.k_end - p.k_begin;
         if (p.period + dmix::kTabPad <= dmix::kDfTabCap) cap = std::max<uint32_t>(cap, p.period + dmix::kTabPad);
     }
-    if (2 * tabled < total) return false;
+    if (mixed) {
+        cap = 0;   // (input that is already mixed: no pieces, no table)
+    } else if (2 * tabled < total) {
+        return false;
+    }
     f.tab_cap = (cap + 1) & ~1u;
     *smem_bytes = (size_t)f.tab_cap * sizeof(float2) + (size_t)slots * sizeof(float2);
     return true;
+}
+
+// The two-pass form's scratch buffer for launches on stream `s`: at least `samples` complex f32.
+float2* decim_scratch(doppler_b200_decim* dec, cudaStream_t s, size_t samples)
+{
+    for (auto& sc : dec->scratch)
+        if (sc.stream == s) {
+            if (sc.cap >= samples) return sc.buf;
+            rt_quiesce(dec->ctx);
+            cudaStreamSynchronize(s);
+            cudaFree(sc.buf);
+            sc.buf = nullptr;
+            sc.cap = 0;
+            if (cudaMalloc(&sc.buf, samples * sizeof(float2)) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            sc.cap = samples;
+            return sc.buf;
+        }
+    float2* buf = nullptr;
+    if (cudaMalloc(&buf, samples * sizeof(float2)) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    dec->scratch.push_back({s, buf, samples});
+    return buf;
 }
 
 // One device-resident call of the fused stage: `runs` over n samples at d_in; outputs to d_out.  Asynchronous on `s`.
@@ -1580,23 +1618,52 @@ int decimate_launch(doppler_b200_decim* dec, const void* d_in, uint64_t n, int i
     static const DecimKernel kern[2][2] = {{dmix::mix_decimate_kernel<0, 0>, dmix::mix_decimate_kernel<0, 1>},
                                            {dmix::mix_decimate_kernel<1, 0>, dmix::mix_decimate_kernel<1, 1>}};
     size_t fsmem = 0;
-    if (nout && dec->fast_ok && !ctx->decim_generic && ((((uintptr_t)d_in) | ((uintptr_t)d_out)) & 15) == 0 &&
-        decim_fast_plan(dec, i0, ctx->decim_stage_slots, dev, &fsmem)) {
-        // register-blocked kernel: 4 consecutive outputs per thread, taps in the kernel parameters (decimate_kernels.cuh)
+    const bool can_fast = nout && dec->fast_ok && !ctx->decim_generic && ((((uintptr_t)d_in) | ((uintptr_t)d_out)) & 15) == 0;
+    auto launch_fast = [&](int in_kind) -> int {   // in_kind: 0 i16, 1 f32, 2 already mixed
         constexpr uint32_t R = dmix::kDfR;
         dmix::DecimFastArgs& f = dec->fast;
-        f.d = a;
         const uint64_t steps = (nout + (uint64_t)R * f.tb - 1) / ((uint64_t)R * f.tb);
         const uint32_t nt = f.tb > 128 ? 256 : 128;   // CTA size: the next instantiated size that holds the output-owning threads
         const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(2048 / nt, (size_t)(227 * 1024) / (fsmem + 1024)));
         const uint32_t grid = (uint32_t)std::min<uint64_t>(steps, (uint64_t)ctx->sm_count * per_sm);
-        const DecimFastKernel fk = intype == DOPPLER_B200_I16
-                                       ? (outtype == DOPPLER_B200_I16 ? dmix::df_kernel_0_0 : dmix::df_kernel_0_1)(nt == 128, (int)f.shape)
-                                       : (outtype == DOPPLER_B200_I16 ? dmix::df_kernel_1_0 : dmix::df_kernel_1_1)(nt == 128, (int)f.shape);
+        static DecimFastKernel (*const pick[3][2])(int, int) = {{dmix::df_kernel_0_0, dmix::df_kernel_0_1},
+                                                                {dmix::df_kernel_1_0, dmix::df_kernel_1_1},
+                                                                {dmix::df_kernel_2_0, dmix::df_kernel_2_1}};
+        const DecimFastKernel fk = pick[in_kind][outtype == DOPPLER_B200_I16 ? 0 : 1](nt == 128, (int)f.shape);
         CUDA_TRY(ctx, cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         fk<<<grid, nt, fsmem, s>>>(f);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
+        return DOPPLER_B200_OK;
+    };
+    bool history_done = false;
+    constexpr uint64_t kTwoPassMax = 1ull << 28;   // 2 GiB of scratch at most
+    if (can_fast && decim_fast_plan(dec, i0, ctx->decim_stage_slots, dev, &fsmem)) {
+        // register-blocked kernel: 4 consecutive outputs per thread, taps in the kernel parameters (decimate_kernels.cuh)
+        dec->fast.d = a;
+        int rc = launch_fast(intype);
+        if (rc) return rc;
+    } else if (can_fast && n <= kTwoPassMax && decim_fast_plan(dec, i0 + ((dec->ntaps - 1 + 3) & ~3u), ctx->decim_stage_slots, dev, &fsmem, /*mixed=*/true)) {
+        // Mostly table-less pieces (long periods, track mode): the mixer itself writes the mixed stream as complex f32 into a
+        // scratch buffer, behind the carried history, and the register-blocked kernel runs over that (decimate_kernels.cuh).
+        const uint32_t nh = dec->ntaps - 1, H = (nh + 3) & ~3u;   // the history ends on a 32-byte boundary
+        float2* y = decim_scratch(dec, s, (size_t)H + n);
+        if (!y) return fail(ctx, DOPPLER_B200_ECUDA, "decimator: no memory for %llu samples of scratch", (unsigned long long)(H + n));
+        if (nh) CUDA_TRY(ctx, cudaMemcpyAsync(y + (H - nh), dec->d_hist[dec->cur], nh * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+        uint32_t sn_mix = *samplenum;
+        int rc = launch_mix(ctx, d_in, y + H, n, intype, DOPPLER_B200_F32, runs, &sn_mix, s);
+        if (rc) return rc;
+        dmix::DecimArgs b = a;
+        memset(&b.mix, 0, sizeof b.mix);
+        b.mix.in = y;
+        b.mix.nsamples = (uint32_t)(H + n);
+        b.first_out = (uint32_t)(i0 + H);
+        dec->fast.d = b;
+        rc = launch_fast(2);
+        if (rc) return rc;
+        // the next call's history: the last ntaps-1 mixed samples (older ones from this call's history when n is short)
+        if (nh) CUDA_TRY(ctx, cudaMemcpyAsync(dec->d_hist[dec->cur ^ 1], y + (H + n - nh), nh * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+        history_done = true;
     } else if (nout) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>((nout + ot - 1) / ot, (uint64_t)ctx->sm_count * 8);
         CUDA_TRY(ctx, cudaFuncSetAttribute(kern[intype][outtype], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1605,13 +1672,15 @@ int decimate_launch(doppler_b200_decim* dec, const void* d_in, uint64_t n, int i
         ctx->launches++;
     }
     if (dec->ntaps > 1) {
-        const uint32_t hgrid = (dec->ntaps - 1 + dmix::kDecimThreads - 1) / dmix::kDecimThreads;
-        if (intype == DOPPLER_B200_I16)
-            dmix::decim_history_kernel<0><<<hgrid, dmix::kDecimThreads, 0, s>>>(a);
-        else
-            dmix::decim_history_kernel<1><<<hgrid, dmix::kDecimThreads, 0, s>>>(a);
-        CUDA_TRY(ctx, cudaGetLastError());
-        ctx->launches++;
+        if (!history_done) {
+            const uint32_t hgrid = (dec->ntaps - 1 + dmix::kDecimThreads - 1) / dmix::kDecimThreads;
+            if (intype == DOPPLER_B200_I16)
+                dmix::decim_history_kernel<0><<<hgrid, dmix::kDecimThreads, 0, s>>>(a);
+            else
+                dmix::decim_history_kernel<1><<<hgrid, dmix::kDecimThreads, 0, s>>>(a);
+            CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches++;
+        }
         CUDA_TRY(ctx, cudaEventRecord(dec->hist_ready, s));
         dec->hist_event_valid = true;
         dec->hist_stream = s;
@@ -1747,6 +1816,8 @@ void doppler_b200_decim_destroy(doppler_b200_decim* d)
     for (float2* h : d->d_hist)
         if (h) cudaFree(h);
     if (d->d_pieces) cudaFree(d->d_pieces);
+    for (auto& sc : d->scratch)
+        if (sc.buf) cudaFree(sc.buf);
     if (d->hist_ready) cudaEventDestroy(d->hist_ready);
     delete d;
 }
