@@ -22,8 +22,8 @@
 //   * the walk is cut into seven segments of constant active output range [klo, khi] (compile-time per filter shape, bounds from
 //     the host), so the inner loops carry no predicates and issue exactly ntaps multiply-adds per output;
 //   * lanes read y at a stride of 4M samples; one padding slot per 4M samples (slot(j) = j + j / 4M) makes the stride odd in
-//     8-byte units, which is bank-conflict free.  The walk crosses a padding slot at warp-uniform positions that depend only on
-//     the launch, so the host cuts the segments there too: the device runs a list of (length, skip) runs.
+//     8-byte units, which is bank-conflict free.  Where the walk crosses a padding slot depends only on the launch, so the host
+//     gives every walk position its slot offset next to its taps.
 // Phase A of a CTA step (mix the samples the step's outputs need into shared memory) runs 16-byte global loads through two
 // register buffers (the next batch is in flight while one is mixed; the first batch of the next step while this step walks)
 // against a copy of the piece's phasor table in shared memory; phase B is the walk.  Several CTAs per SM overlap each other's
@@ -54,30 +54,24 @@ constexpr int C32 = 2;                  // a third "input type" of this kernel: 
 constexpr int kDfR = 4;                 // outputs per thread
 constexpr int kDfMaxThreads = 256;
 constexpr int kDfMaxTq = 224;           // walk positions (3M + ntaps) the parameter block holds
-constexpr int kDfMaxRuns = 72;          // 7 segments + one cut per padding slot crossed (at most 224 / 4 + 1)
 constexpr uint32_t kDfStageSlots = 8448;   // shared-memory slots (8 B) of one CTA step by default: 66 KB, three CTAs per SM
 constexpr uint32_t kDfTabCap = 1024;       // phasor-table entries (8 B) a CTA keeps in shared memory; longer tables are read through L1
 
-struct DfRun {
-    uint16_t n;      // walk positions of this run
-    uint16_t skip;   // padding slots crossed after it (0 or 1)
-};
-
 struct alignas(16) DfTaps {
     uint64_t h[kDfR];   // h[k] = (tap, tap) of output k at this walk position: tap index u - (3 - k) * M, 0 outside the filter
+    uint32_t off;       // byte offset, from the thread's base slot tid * (4M + 1), of the sample this position reads: (c + c / 4M) * 8
+    uint32_t pad[3];
 };
 
 struct DecimFastArgs {
     DecimArgs d;
     uint32_t tb;          // threads of a CTA that own outputs (a multiple of 32, <= the CTA size): a CTA step makes 4 * tb outputs
     uint32_t lead;        // staged sample 0 is call-relative sample i0 - lead, so that it is a multiple of 4 (16-byte loads)
-    uint32_t slot0;       // slot, relative to a thread's base tid * (4M + 1), of walk position 0: c0 + c0 / 4M, c0 = lead + ntaps - 1 + 3M
     uint32_t shape;       // min(3, (ntaps - 1) / M): selects the kernel instantiation
     uint32_t rm_magic;    // j / 4M == umulhi(j, rm_magic) for the staged indices of a step
     uint32_t tab_cap;     // phasor-table entries the launch reserves in shared memory (0: tables stay in global memory)
-    uint32_t nruns[8];    // runs of segment i (consecutive in `runs`); segment i = [cuts[i], cuts[i+1]) of the sorted bounds
-                          // {0, M, 2M, 3M, ntaps, M + ntaps, 2M + ntaps, 3M + ntaps}
-    DfRun runs[kDfMaxRuns];
+    uint32_t cuts[8];     // the walk's segment bounds: {0, M, 2M, 3M, ntaps, M + ntaps, 2M + ntaps, 3M + ntaps} sorted;
+                          // segment i = positions [cuts[i], cuts[i+1])
     DfTaps tq[kDfMaxTq];
 };
 
@@ -107,56 +101,6 @@ __device__ __forceinline__ uint32_t opaque_u32(uint32_t v)
     return r;
 }
 
-// n walk positions from u on, outputs KLO .. KHI active; p = shared address of this thread's slot of position u
-// (u is a signed int so that the tap addresses of an unrolled body fold into immediate offsets of one uniform register)
-template <int KLO, int KHI>
-__device__ __forceinline__ void df_walk(const DecimFastArgs& A, uint32_t& p, int& u, uint32_t n, uint64_t (&acc)[kDfR])
-{
-    auto load4 = [&](uint64_t (&y)[4]) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) y[i] = lds_u64(p - 8u * i);
-        p -= 32u;
-    };
-    auto fma4 = [&](const uint64_t (&y)[4]) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-#pragma unroll
-            for (int k = KLO; k <= KHI; ++k) acc[k] = fma_f32x2(A.tq[u + i].h[k], y[i], acc[k]);
-        }
-        u += 4;
-    };
-    // software-pipelined: the next four samples are read before the current four are consumed (2-6 % over the plain loop,
-    // interleaved A/B on one box: 0.705 -> 0.68 ms at M = 8, 0.853 -> 0.80 ms at M = 4)
-    if (n >= 4u) {
-        uint64_t ya[4], yb[4];
-        load4(ya);
-        n -= 4u;
-        while (n >= 8u) {
-            load4(yb);
-            fma4(ya);
-            load4(ya);
-            fma4(yb);
-            n -= 8u;
-        }
-        if (n >= 4u) {
-            load4(yb);
-            fma4(ya);
-            fma4(yb);
-            n -= 4u;
-        } else {
-            fma4(ya);
-        }
-    }
-    for (; n; --n) {   // (reading these 1 .. 3 samples together under run-time guards was tried: the guards cost the tap reads
-                       // their place on the uniform datapath, 0.68 -> 1.2 ms)
-        const uint64_t y = lds_u64(p);
-#pragma unroll
-        for (int k = KLO; k <= KHI; ++k) acc[k] = fma_f32x2(A.tq[u].h[k], y, acc[k]);
-        ++u;
-        p -= 8u;
-    }
-}
-
 // The walk's seven segments.  Output k is active at positions [(3 - k) * M, (3 - k) * M + ntaps); the eight bounds sorted are
 // the segments' cuts, and which outputs are active between two neighbouring cuts depends only on
 // SHAPE = min(3, (ntaps - 1) / M) -- so the ranges are compile-time and the dispatch is straight-line code (a switch on a
@@ -173,29 +117,63 @@ struct DfRange {
     static constexpr int hi = SHAPE == 3 ? hi3[I] : SHAPE == 2 ? hi2[I] : SHAPE == 1 ? hi1[I] : hi0[I];
 };
 
-template <int SHAPE, int I>
-__device__ __forceinline__ void df_segment(const DecimFastArgs& A, uint32_t& p, int& u, uint32_t& ri, uint64_t (&acc)[kDfR])
+// Walk positions [u, ue) with outputs KLO .. KHI active; pbase = shared address of the thread's base slot.  The padding slots
+// are folded into a per-position offset (DfTaps::off, one more uniform load per position), so a segment is ONE loop whatever
+// padding it crosses.  (A first form cut the segments into runs at the padding slots and stepped a pointer: the 1 .. 3-position
+// remainders of those runs each exposed a full shared-memory latency -- 5-11 % slower, interleaved A/B.)  Software-pipelined:
+// the next four samples are read before the current four are consumed (another 2-6 %).  u is a signed int so that the tap
+// addresses of an unrolled body fold into immediate offsets of one uniform register.
+template <int KLO, int KHI>
+__device__ __forceinline__ void df_walk(const DecimFastArgs& A, uint32_t pbase, int u, int ue, uint64_t (&acc)[kDfR])
 {
-    const uint32_t re = ri + A.nruns[I];
-    for (; ri < re; ri++) {
-        const DfRun r = A.runs[ri];
-        df_walk<DfRange<SHAPE, I>::lo, DfRange<SHAPE, I>::hi>(A, p, u, r.n, acc);
-        p -= 8u * r.skip;
+    auto load4 = [&](uint64_t (&y)[4], int at) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) y[i] = lds_u64(pbase + A.tq[at + i].off);
+    };
+    auto fma4 = [&](const uint64_t (&y)[4], int at) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int k = KLO; k <= KHI; ++k) acc[k] = fma_f32x2(A.tq[at + i].h[k], y[i], acc[k]);
+        }
+    };
+    if (u + 4 <= ue) {
+        uint64_t ya[4], yb[4];
+        load4(ya, u);
+        while (u + 12 <= ue) {
+            load4(yb, u + 4);
+            fma4(ya, u);
+            load4(ya, u + 8);
+            fma4(yb, u + 4);
+            u += 8;
+        }
+        if (u + 8 <= ue) {
+            load4(yb, u + 4);
+            fma4(ya, u);
+            fma4(yb, u + 4);
+            u += 8;
+        } else {
+            fma4(ya, u);
+            u += 4;
+        }
+    }
+    for (; u < ue; ++u) {
+        const uint64_t y = lds_u64(pbase + A.tq[u].off);
+#pragma unroll
+        for (int k = KLO; k <= KHI; ++k) acc[k] = fma_f32x2(A.tq[u].h[k], y, acc[k]);
     }
 }
 
 template <int SHAPE>
-__device__ __forceinline__ void df_walk_all(const DecimFastArgs& A, uint32_t p, uint64_t (&acc)[kDfR])
+__device__ __forceinline__ void df_walk_all(const DecimFastArgs& A, uint32_t pbase, uint64_t (&acc)[kDfR])
 {
-    int u = 0;
-    uint32_t ri = 0;
-    df_segment<SHAPE, 0>(A, p, u, ri, acc);
-    df_segment<SHAPE, 1>(A, p, u, ri, acc);
-    df_segment<SHAPE, 2>(A, p, u, ri, acc);
-    df_segment<SHAPE, 3>(A, p, u, ri, acc);
-    df_segment<SHAPE, 4>(A, p, u, ri, acc);
-    df_segment<SHAPE, 5>(A, p, u, ri, acc);
-    df_segment<SHAPE, 6>(A, p, u, ri, acc);
+    df_walk<DfRange<SHAPE, 0>::lo, DfRange<SHAPE, 0>::hi>(A, pbase, (int)A.cuts[0], (int)A.cuts[1], acc);
+    df_walk<DfRange<SHAPE, 1>::lo, DfRange<SHAPE, 1>::hi>(A, pbase, (int)A.cuts[1], (int)A.cuts[2], acc);
+    df_walk<DfRange<SHAPE, 2>::lo, DfRange<SHAPE, 2>::hi>(A, pbase, (int)A.cuts[2], (int)A.cuts[3], acc);
+    df_walk<DfRange<SHAPE, 3>::lo, DfRange<SHAPE, 3>::hi>(A, pbase, (int)A.cuts[3], (int)A.cuts[4], acc);
+    df_walk<DfRange<SHAPE, 4>::lo, DfRange<SHAPE, 4>::hi>(A, pbase, (int)A.cuts[4], (int)A.cuts[5], acc);
+    df_walk<DfRange<SHAPE, 5>::lo, DfRange<SHAPE, 5>::hi>(A, pbase, (int)A.cuts[5], (int)A.cuts[6], acc);
+    df_walk<DfRange<SHAPE, 6>::lo, DfRange<SHAPE, 6>::hi>(A, pbase, (int)A.cuts[6], (int)A.cuts[7], acc);
 }
 
 // one 16-byte group (4 i16 or 2 f32 samples) against table entries ph, ph + 1, ...: mixed samples to shared address dst
@@ -371,7 +349,7 @@ __global__ void __launch_bounds__(NT) mix_decimate_fast_kernel(const __grid_cons
             uint64_t acc[R];
 #pragma unroll
             for (int k = 0; k < R; k++) acc[k] = 0ull;   // (+0.0f, +0.0f)
-            df_walk_all<SHAPE>(A, ys_addr + (tid * (RM + 1u) + A.slot0) * 8u, acc);
+            df_walk_all<SHAPE>(A, ys_addr + tid * (RM + 1u) * 8u, acc);
             const uint32_t m0 = tid * R;
             float2 z[R];
 #pragma unroll

@@ -1465,8 +1465,8 @@ void decim_fast_setup(doppler_b200_decim* d, const float* taps)
     d->fast_ok = true;
 }
 
-// ... and what depends on the call: threads per CTA from the stage budget, the staging origin, and the walk's runs (the segments
-// cut again where the walk crosses a padding slot).  False when the launch does not fit (the generic kernel takes it).
+// ... and what depends on the call: threads per CTA from the stage budget, the staging origin, and with it every walk position's
+// slot offset.  False when the launch does not fit (the generic kernel takes it).
 bool decim_fast_plan(doppler_b200_decim* d, uint64_t i0, uint32_t stage_slots, const std::vector<DevPiece>& pieces, size_t* smem_bytes,
                      bool mixed = false)
 {
@@ -1484,20 +1484,12 @@ bool decim_fast_plan(doppler_b200_decim* d, uint64_t i0, uint32_t stage_slots, c
     }
     if (tb < 32) return false;
     f.tb = tb;
+    // walk position u reads staged index c0 - u of the thread's group: its slot offset (one padding slot per 4M) rides with its taps
     const uint32_t c0 = f.lead + (ntaps - 1) + (R - 1) * M;
-    f.slot0 = c0 + c0 / RM;
-    uint32_t ri = 0;
-    for (int i = 0; i < 7; i++) {
-        f.nruns[i] = 0;
-        for (uint32_t u = d->cuts[i]; u < d->cuts[i + 1];) {
-            const uint32_t cm = (c0 - u) % RM, left = d->cuts[i + 1] - u;   // cm more positions before the next padding slot
-            const bool cross = cm < left;
-            const uint32_t n = cross ? cm + 1 : left;
-            if (ri == (uint32_t)dmix::kDfMaxRuns) return false;
-            f.runs[ri++] = dmix::DfRun{(uint16_t)n, (uint16_t)(cross ? 1 : 0)};
-            f.nruns[i]++;
-            u += n;
-        }
+    for (int i = 0; i < 8; i++) f.cuts[i] = d->cuts[i];
+    for (uint32_t u = 0; u < (R - 1) * M + ntaps; u++) {
+        const uint32_t c = c0 - u;
+        f.tq[u].off = (c + c / RM) * 8u;
     }
     // the longest tabled period that fits the CTA's table area decides its size; a launch whose samples mostly lie in pieces
     // WITHOUT a table (long periods, track mode) gains nothing from this kernel's staging loop and keeps the generic kernel
@@ -1867,27 +1859,20 @@ long doppler_b200_decim_walk_trace(const float* taps, uint32_t ntaps, uint32_t d
                       dmix::DfRange<1, 2>::lo == 2 && dmix::DfRange<1, 2>::hi == 2 && dmix::DfRange<2, 3>::lo == 1 && dmix::DfRange<2, 3>::hi == 2,
                   "walk ranges");
     const uint32_t c0 = f.lead + (ntaps - 1) + (R - 1) * M;
-    int64_t slot = (int64_t)f.slot0;   // relative to the thread's base slot tid * (4M + 1)
-    uint32_t u = 0, ri = 0;
     size_t n = 0;
     for (int i = 0; i < 7; i++) {
-        for (uint32_t r = 0; r < f.nruns[i]; r++, ri++) {
-            for (uint32_t x = 0; x < f.runs[ri].n; x++, u++, slot--) {
-                if (n < cap) {
-                    uint32_t* rec = records + n * 8;
-                    rec[0] = c0 - u;
-                    rec[1] = (uint32_t)slot;
-                    rec[2] = (uint32_t)lo[f.shape][i];
-                    rec[3] = (uint32_t)hi[f.shape][i];
-                    for (uint32_t k = 0; k < R; k++) {
-                        const bool on = (int)k >= lo[f.shape][i] && (int)k <= hi[f.shape][i];
-                        rec[4 + k] = on ? u - (R - 1 - k) * M : 0xffffffffu;
-                        if (tap_bits) tap_bits[n * 4 + k] = (uint32_t)f.tq[u].h[k];
-                    }
-                }
-                n++;
+        for (uint32_t u = f.cuts[i]; u < f.cuts[i + 1]; u++, n++) {
+            if (n >= cap) continue;
+            uint32_t* rec = records + n * 8;
+            rec[0] = c0 - u;
+            rec[1] = f.tq[u].off / 8u;   // relative to the thread's base slot tid * (4M + 1)
+            rec[2] = (uint32_t)lo[f.shape][i];
+            rec[3] = (uint32_t)hi[f.shape][i];
+            for (uint32_t k = 0; k < R; k++) {
+                const bool on = (int)k >= lo[f.shape][i] && (int)k <= hi[f.shape][i];
+                rec[4 + k] = on ? u - (R - 1 - k) * M : 0xffffffffu;
+                if (tap_bits) tap_bits[n * 4 + k] = (uint32_t)f.tq[u].h[k];
             }
-            slot -= f.runs[ri].skip;
         }
     }
     (void)RM;
