@@ -36,14 +36,14 @@
 // than evaluating one generic sincosf per sample here.  Launches outside the envelope (too many taps for the parameter block,
 // M > 64, unaligned buffers) keep the generic kernel, mix_decimate_kernel.
 //
-// Measured (B200, 256 M samples, tools/decim_bench.py, profiles/r02_decim_*): const f32 -> i16, M = 8, 49 taps 0.66-0.68 ms =
-// 380 Gsample/s in = 0.50 of the stage's HBM roofline (first version: 1.78 ms, 0.19); i16 -> i16 0.25 of its 4.5 B/sample
-// roofline.  ncu: 53 issued instructions per input sample at 57 % issue utilisation, load/store-unit wavefronts at 66 %
-// (two-thirds of them shared memory), 24 warps per SM -- the stage is bound by issue slots and the shared-memory pipe
-// together, not by HBM (39 % of peak).  Two restructurings that cut both counters but LOST on the clock, kept out of the tree:
-// two lockstep output groups per thread (tap loads and loop control shared by eight chains: 39 instructions per sample, but half
-// the warps per SM for the same shared memory: 0.75-0.80 ms) and one sample per lane in phase A (conflict-free shared memory,
-// same result).  Shared memory per resident warp is what limits the stage.
+// Measured (B200, 256 M samples, tools/decim_bench.py, profiles/r02_decim_*): const f32 -> i16, M = 8, 49 taps 0.65 ms =
+// 393 Gsample/s in = 0.52 of the stage's HBM roofline (first version: 1.78 ms, 0.19); i16 -> i16 0.26 of its 4.5 B/sample
+// roofline; table-less launches (two passes) 1.18 ms, 0.28.  ncu: 52 issued instructions per input sample at 59 % issue
+// utilisation, load/store-unit wavefronts at 66 % (two-thirds of them shared memory), 24 warps per SM -- the stage is bound by
+// issue slots and the shared-memory pipe together, not by HBM (40 % of peak).  Restructurings that cut those counters but LOST
+// on the clock, kept out of the tree: two lockstep output groups per thread (tap loads and loop control shared by eight
+// chains: 39 instructions per sample, but half the warps per SM for the same shared memory: 0.75-0.80 ms) and one sample per
+// lane in phase A (conflict-free shared memory, same result).  Shared memory per resident warp is what limits the stage.
 #pragma once
 
 #include "mixer_kernels.cuh"
