@@ -906,15 +906,20 @@ int rt_request(doppler_b200_ctx* ctx, const MixArgs& a, int intype, int outtype)
         if (rc) return rc;
         mb = ctx->rt_mb;
     }
-    // the request in tagged 64-byte lines: payload first, then the line's tag (mixer_kernels.cuh: RtMailbox)
-    uint32_t payload[dmix::kRtLines * 15] = {0};
+    // the request in tagged 64-byte lines: payload (types, MixArgs, the sum of those words) first, then the line's tag
+    // (mixer_kernels.cuh: RtMailbox)
+    constexpr int kW = dmix::kRtUnit - 1;   // payload words per line
+    uint32_t payload[dmix::kRtSectors * kW] = {0};
     payload[0] = (uint32_t)intype;
     payload[1] = (uint32_t)outtype;
     memcpy(payload + 2, &a, sizeof a);
+    uint32_t sum = 0;
+    for (int i = 0; i < dmix::kRtPayloadWords - 1; i++) sum += payload[i];
+    payload[dmix::kRtPayloadWords - 1] = sum;
     const uint32_t seq = ++ctx->rt_seq ? ctx->rt_seq : ++ctx->rt_seq;   // (0 is the mailbox's initial state)
-    for (int l = 0; l < dmix::kRtLines; l++) {
+    for (int l = 0; l < dmix::kRtSectors; l++) {
         volatile uint32_t* line = mb->req[l].w;
-        for (int i = 0; i < 15; i++) line[i] = payload[l * 15 + i];
+        for (int i = 0; i < kW; i++) line[i] = payload[l * kW + i];
         std::atomic_thread_fence(std::memory_order_release);
         *const_cast<volatile uint32_t*>(&mb->req[l].tag) = seq;
     }

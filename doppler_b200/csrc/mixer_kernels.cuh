@@ -1569,25 +1569,36 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
 // `idle_ns` without a request (alive = 0, after one last look at seq), and at once when the host sets quit; the host starts
 // another when it finds alive == 0.  Only launches whose pieces fit MixArgs::inl come here.
 // Mailbox layout.  Every round trip over PCIe costs ~2 us, so a request must be visible to the device in ONE read: the request
-// (types + MixArgs) travels in 64-byte lines whose last word is the request number.  A PCIe read returns a coherent snapshot of
-// a cache line, and the host writes a line's payload before its tag (x86 stores are ordered), so a line whose tag is n carries
-// request n; the CTA reads all lines in one wave and takes the request when every tag shows the same new number.
-constexpr int kRtPayloadWords = 2 + (int)(sizeof(MixArgs) / 4);   // intype, outtype, MixArgs
-constexpr int kRtLines = (kRtPayloadWords + 14) / 15;
-struct RtLine {
-    uint32_t w[15];
+// (types + MixArgs + a checksum) travels in 64-byte lines whose last word is the request number.  The sixteen lanes that read
+// a line do so in one warp instruction, a read of a cache line returns a coherent snapshot, and the host writes a line's payload
+// before its tag (x86 stores are ordered) -- so a line whose tag is n carries request n, and the CTA reads all lines in one wave
+// and takes the request when every tag shows the same new number.  Nothing promises that the memory system fetches a line in
+// ONE request rather than as two 32-byte sectors at different times (the first of which could then predate the host's write
+// while the second shows the new tag), so the payload also carries the sum of its words: a wave that mixes words of two
+// requests is rejected unless the mixed words are equal anyway, and simply looked at again.  (One tag per 32-byte sector needs
+// no such argument, but doubles the read requests of a wave: 10.1 us per block against 8.2-9.5 interleaved on one box, no
+// difference on a slower one; DOPPLER_RT_SECTOR_TAGS builds it.)
+constexpr int kRtPayloadWords = 3 + (int)(sizeof(MixArgs) / 4);   // intype, outtype, MixArgs, checksum (last)
+#ifdef DOPPLER_RT_SECTOR_TAGS   // A/B build: one tag per 32-byte sector
+constexpr int kRtUnit = 8;
+#else
+constexpr int kRtUnit = 16;                                         // words per tagged unit: a 64-byte line
+#endif
+constexpr int kRtSectors = (kRtPayloadWords + kRtUnit - 2) / (kRtUnit - 1);
+struct RtSector {
+    uint32_t w[kRtUnit - 1];
     uint32_t tag;
 };
 struct RtMailbox {
-    RtLine req[kRtLines];       // host -> device
+    RtSector req[kRtSectors];   // host -> device
     volatile uint32_t quit;     // host -> device: leave now                                           (its own cache line)
     uint32_t pad0[15];
     volatile uint32_t served;   // device -> host: latest request whose output is visible to the host   (its own cache line)
     volatile uint32_t alive;    // generation of the resident kernel (the host writes it before the launch); the kernel clears it when it leaves
     uint32_t pad1[14];
 };
-static_assert(sizeof(RtLine) == 64 && sizeof(MixArgs) % 4 == 0, "mailbox lines");
-static_assert((kRtLines + 1) * 16 <= kSmallThreads, "one mailbox word per thread");
+static_assert(sizeof(RtSector) == 4 * kRtUnit && sizeof(MixArgs) % 4 == 0, "mailbox lines");
+static_assert(kRtSectors * kRtUnit + 1 <= kSmallThreads, "one mailbox word per thread");
 
 __device__ __forceinline__ uint64_t global_timer_ns()
 {
@@ -1598,8 +1609,9 @@ __device__ __forceinline__ uint64_t global_timer_ns()
 
 static __global__ void __launch_bounds__(kSmallThreads, 1) mix_resident_kernel(RtMailbox* mb, uint64_t idle_ns, uint32_t gen)
 {
-    __shared__ __align__(16) uint32_t s_words[kRtLines * 15 + 2];   // the request's payload: intype, outtype, MixArgs
-    __shared__ uint32_t s_tag[kRtLines];
+    __shared__ __align__(16) uint32_t s_words[kRtSectors * (kRtUnit - 1) + 2];   // the request's payload: intype, outtype, MixArgs
+    __shared__ uint32_t s_tag[kRtSectors];
+    __shared__ int s_part[kSmallThreads / 32];
     __shared__ uint32_t s_quit, s_idle;
     const uint32_t tid = threadIdx.x;
     const volatile uint32_t* words = reinterpret_cast<const volatile uint32_t*>(mb);
@@ -1607,26 +1619,41 @@ static __global__ void __launch_bounds__(kSmallThreads, 1) mix_resident_kernel(R
     uint64_t t0 = global_timer_ns();
     bool last_look = false;
     for (;;) {
-        // one wave over the mailbox: thread t reads word t of the request lines, thread kRtLines*16 the quit word
-        if (tid < (uint32_t)kRtLines * 16u) {
+        // one wave over the mailbox: thread t reads word t of the request lines, thread kRtSectors*kRtUnit the quit word
+        int contrib = 0;   // payload words add up to the checksum word
+        if (tid < (uint32_t)(kRtSectors * kRtUnit)) {
             const uint32_t v = words[tid];
-            if ((tid & 15u) == 15u)
-                s_tag[tid >> 4] = v;
-            else
-                s_words[(tid >> 4) * 15u + (tid & 15u)] = v;
-        } else if (tid == (uint32_t)kRtLines * 16u) {
+            const uint32_t w = (tid / kRtUnit) * (kRtUnit - 1) + tid % kRtUnit;   // payload index (of the words that are not tags)
+            if (tid % kRtUnit == kRtUnit - 1) {
+                s_tag[tid / kRtUnit] = v;
+            } else {
+                s_words[w] = v;
+                if (w < (uint32_t)kRtPayloadWords - 1u)
+                    contrib = (int)v;
+                else if (w == (uint32_t)kRtPayloadWords - 1u)
+                    contrib = -(int)v;
+            }
+        } else if (tid == (uint32_t)(kRtSectors * kRtUnit)) {
             s_quit = mb->quit;
             s_idle = global_timer_ns() - t0 > idle_ns ? 1u : 0u;
         }
+        const int wsum = __reduce_add_sync(0xffffffffu, contrib);
+        if ((tid & 31u) == 0) s_part[tid >> 5] = wsum;
         __syncthreads();
         const uint32_t seq = s_tag[0];
         bool whole = true;
 #pragma unroll
-        for (int i = 1; i < kRtLines; i++) whole = whole && s_tag[i] == seq;
-        const bool fresh = whole && seq != last;
+        for (int i = 1; i < kRtSectors; i++) whole = whole && s_tag[i] == seq;
+        int total = 0;
+#pragma unroll
+        for (int i = 0; i < kSmallThreads / 32; i++) total += s_part[i];
+#ifdef DOPPLER_RT_NO_CHECKSUM   // A/B build
+        total = 0;
+#endif
+        const bool fresh = whole && seq != last && total == 0;
         const bool quit = s_quit != 0, idle = s_idle != 0;
         if (fresh) {
-            const MixArgs& sa = *reinterpret_cast<const MixArgs*>(s_words + 2);
+            const MixArgs& sa = *reinterpret_cast<const MixArgs*>(s_words + 2);   // (8-byte aligned: s_words is 16-byte aligned)
             switch ((s_words[0] << 1) | s_words[1]) {
             case 0: small_body<I16, I16, 4, true>(sa, 0, 1); break;
             case 1: small_body<I16, F32, 4, true>(sa, 0, 1); break;
