@@ -1,0 +1,13 @@
+// doppler_b200/csrc/collect.h -- host side of the resident kernel's fence-free hand-over (mixer_kernels.cuh: mix_resident_kernel).
+// The device writes its result as 8-byte units {word, request number}; a word has arrived when its neighbour shows the number.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace dcollect {
+// Result words [from, n) of request `seq` out of their units into `out` (any alignment), as far as they have arrived.
+// Returns the index of the first word that has not (n when the result is complete).
+size_t collect(const uint32_t* units, uint32_t seq, unsigned char* out, size_t from, size_t n);
+// (tests) the scalar path alone
+size_t collect_scalar(const uint32_t* units, uint32_t seq, unsigned char* out, size_t from, size_t n);
+}   // namespace dcollect

@@ -29,6 +29,7 @@
 #include "mixer_kernels.cuh"
 #include "decimate_kernels.cuh"
 #include "plan.h"
+#include "collect.h"
 
 // (WARPS, S, U) of the segmented kernel per type pair, chosen on B200 (profiles/r01_seg_tune.md: warps
 // a multiple of the 4 schedulers, 12-16 samples per lane per tile so that the per-tile pipeline overhead is
@@ -150,11 +151,23 @@ struct doppler_b200_ctx {
     dmix::RtMailbox* rt_mb = nullptr;       // mapped pinned host memory
     dmix::RtMailbox* rt_mb_dev = nullptr;   // its device alias
     cudaStream_t rt_stream = nullptr;
-    uint32_t rt_seq = 0, rt_gen = 0;
+    uint32_t* rt_out = nullptr;             // the result in flagged units {word, request number}: mapped pinned host memory
+    void* rt_out_dev = nullptr;
+    const void* rt_in_dev = nullptr;        // what the running kernel was launched with (a request with other addresses restarts it)
+    const void* rt_tables_dev = nullptr;
+    uint32_t rt_seq = 0, rt_gen = 0;        // rt_seq: the latest request, served in full once rt_request has returned
     uint64_t rt_idle_us = 20000;            // the kernel leaves after this long without a request; 0: no resident kernel (doppler_b200_tune)
     uint64_t rt_requests = 0, rt_starts = 0;
-    uint64_t rt_traced = 0;
-    uint64_t rt_ns[4] = {0, 0, 0, 0};       // DOPPLER_B200_TRACE=1: stage in, plan, request -> served, copy out (resident-kernel calls only)
+    // The steady state of a block stream with one shift -- samplenum inside its period, ONE periodic piece per block --
+    // planned without the planner: what the last such block's plan looked like (tiny_host_call).
+    struct RtSteady {
+        bool valid = false, off = false;   // off: DOPPLER_B200_NO_STEADY_RULE=1 (A/B)
+        uint32_t r_bits = 0;
+        DevPiece piece;   // period, r, tab, magic, shift of that plan (k_begin .. base are per block)
+    } rt_steady;
+    uint64_t rt_traced = 0, rt_steady_traced = 0;
+    uint64_t rt_steady_ns[3] = {0, 0, 0};   // the same for calls planned by the steady-state rule (tiny_host_call)
+    uint64_t rt_ns[3] = {0, 0, 0};          // DOPPLER_B200_TRACE=1: stage in, plan, request -> result collected in the caller's buffer (resident-kernel calls only)
     // DOPPLER_B200_TRACE=1: phase clock of the tiny host path (ns totals: staging in, plan + launch, wait for the flag, copy out)
     bool trace = false;
     uint64_t tiny_calls = 0, tiny_ns[4] = {0, 0, 0, 0};
@@ -311,6 +324,7 @@ int get_table(doppler_b200_ctx* ctx, float r, uint32_t period, uint64_t piece_le
         CUDA_TRY(ctx, cudaDeviceSynchronize());
         ctx->arena_used = 0;
         ctx->tables.clear();
+        ctx->rt_steady.valid = false;   // (it remembers a table offset)
     }
     const uint32_t off = (uint32_t)ctx->arena_used;
     const uint32_t blocks = (uint32_t)((entries + dmix::kThreads - 1) / dmix::kThreads);
@@ -666,7 +680,7 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
                 a.seg_index = reinterpret_cast<const uint32_t*>(d_meta + off_index);
             }
         }
-        if (small && rt_args && !up_pieces && l0 == 0 && l1 == nsamples) {
+        if (small && rt_args && a.npieces <= (uint32_t)dmix::kRtPieces && l0 == 0 && l1 == nsamples) {
             *rt_args = a;
             *rt_filled = true;
             *samplenum = sn_after;
@@ -863,7 +877,11 @@ int device_alias(doppler_b200_ctx* ctx, const void* host, void** dev)
 }
 
 // ---- resident kernel (mixer_kernels.cuh: mix_resident_kernel) --------------------------------------------------------------
-int rt_start(doppler_b200_ctx* ctx)
+constexpr size_t kRtOutUnits = 2 * kTinyStageBytes / 4;   // result words of the largest block served (i16 -> f32 doubles the bytes)
+
+// A kernel that reads blocks at `in_dev` and tables at `tables_dev`, and has served every request up to ctx->rt_seq (`pending`:
+// up to the one before -- the mailbox already holds ctx->rt_seq for it).
+int rt_start(doppler_b200_ctx* ctx, const void* in_dev, const void* tables_dev, bool pending)
 {
     if (!ctx->rt_mb) {
         CUDA_TRY(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->rt_mb), sizeof(dmix::RtMailbox), cudaHostAllocMapped));
@@ -871,70 +889,97 @@ int rt_start(doppler_b200_ctx* ctx)
         void* alias = nullptr;
         CUDA_TRY(ctx, cudaHostGetDevicePointer(&alias, ctx->rt_mb, 0));
         ctx->rt_mb_dev = static_cast<dmix::RtMailbox*>(alias);
+        CUDA_TRY(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->rt_out), kRtOutUnits * 8, cudaHostAllocMapped));
+        memset(ctx->rt_out, 0, kRtOutUnits * 8);   // (no unit carries a request number yet: they start at 1)
+        CUDA_TRY(ctx, cudaHostGetDevicePointer(&ctx->rt_out_dev, ctx->rt_out, 0));
         // highest priority: when the chip is full of another stream's CTAs, the one resident CTA is placed first
         int prio_lo = 0, prio_hi = 0;
         CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->rt_stream, cudaStreamNonBlocking, prio_hi));
     }
     const uint32_t gen = ++ctx->rt_gen ? ctx->rt_gen : ++ctx->rt_gen;   // never 0
+    uint32_t last = ctx->rt_seq;
+    if (pending) last = (last - 1u) ? last - 1u : last - 2u;   // (request numbers skip 0)
     ctx->rt_mb->alive = gen;
+    ctx->rt_in_dev = in_dev;
+    ctx->rt_tables_dev = tables_dev;
     std::atomic_thread_fence(std::memory_order_seq_cst);
     // (queued behind a predecessor that is still leaving: same stream)
-    dmix::mix_resident_kernel<<<1, dmix::kSmallThreads, 0, ctx->rt_stream>>>(ctx->rt_mb_dev, ctx->rt_idle_us * 1000ull, gen);
+    dmix::mix_resident_kernel<<<1, dmix::kSmallThreads, 0, ctx->rt_stream>>>(ctx->rt_mb_dev, in_dev, ctx->rt_out_dev, static_cast<const float2*>(tables_dev),
+                                                                            ctx->rt_idle_us * 1000ull, gen, last);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     ctx->rt_starts++;
     return DOPPLER_B200_OK;
 }
 
-// The resident kernel leaves now (before anything that synchronises the device, frees memory it may read, or ends the context).
-void rt_quiesce(doppler_b200_ctx* ctx)
+// A request in the mailbox's tagged lines: payload first, then the line's tag (mixer_kernels.cuh: RtMailbox).
+static uint32_t rt_post(doppler_b200_ctx* ctx, uint32_t head, const MixArgs* a)
 {
-    if (!ctx->rt_mb) return;
-    ctx->rt_mb->quit = 1;
-    std::atomic_thread_fence(std::memory_order_seq_cst);
-    cudaStreamSynchronize(ctx->rt_stream);
-    ctx->rt_mb->quit = 0;
-    ctx->rt_mb->alive = 0;
-    cudaGetLastError();
-}
-
-// One request through the mailbox; returns when its output is visible in host memory.
-int rt_request(doppler_b200_ctx* ctx, const MixArgs& a, int intype, int outtype)
-{
-    dmix::RtMailbox* mb = ctx->rt_mb;
-    if (!mb || mb->alive == 0) {
-        int rc = rt_start(ctx);
-        if (rc) return rc;
-        mb = ctx->rt_mb;
+    constexpr int kW = 15;   // payload words per line
+    uint32_t payload[dmix::kRtLines * kW] = {0};
+    payload[0] = head;
+    if (a) {
+        payload[1] = a->nsamples;
+        for (uint32_t p = 0; p < a->npieces; p++) memcpy(payload + 2 + p * dmix::kRtPieceWords, &a->inl[p], dmix::kRtPieceWords * 4);
     }
-    // the request in tagged 64-byte lines: payload (types, MixArgs, the sum of those words) first, then the line's tag
-    // (mixer_kernels.cuh: RtMailbox)
-    constexpr int kW = dmix::kRtUnit - 1;   // payload words per line
-    uint32_t payload[dmix::kRtSectors * kW] = {0};
-    payload[0] = (uint32_t)intype;
-    payload[1] = (uint32_t)outtype;
-    memcpy(payload + 2, &a, sizeof a);
     uint32_t sum = 0;
     for (int i = 0; i < dmix::kRtPayloadWords - 1; i++) sum += payload[i];
     payload[dmix::kRtPayloadWords - 1] = sum;
-    const uint32_t seq = ++ctx->rt_seq ? ctx->rt_seq : ++ctx->rt_seq;   // (0 is the mailbox's initial state)
-    for (int l = 0; l < dmix::kRtSectors; l++) {
+    dmix::RtMailbox* mb = ctx->rt_mb;
+    uint32_t seq = ++ctx->rt_seq;
+    if (seq == 0) {
+        // the numbers wrap: no unit may still carry one that is about to be used again (the kernel is idle: every request
+        // before this one has been collected, and nothing writes units between requests)
+        memset(ctx->rt_out, 0, kRtOutUnits * 8);
+        seq = ++ctx->rt_seq;   // (0 is the mailbox's initial state)
+    }
+    for (int l = 0; l < dmix::kRtLines; l++) {
         volatile uint32_t* line = mb->req[l].w;
         for (int i = 0; i < kW; i++) line[i] = payload[l * kW + i];
         std::atomic_thread_fence(std::memory_order_release);
         *const_cast<volatile uint32_t*>(&mb->req[l].tag) = seq;
     }
+    std::atomic_thread_fence(std::memory_order_seq_cst);   // (out of the store buffer now, not when the spin loop's loads let it)
+    return seq;
+}
+
+// The resident kernel leaves now (before anything that synchronises the device, frees memory it may read, or ends the context).
+void rt_quiesce(doppler_b200_ctx* ctx)
+{
+    if (!ctx->rt_mb) return;
+    if (ctx->rt_mb->alive != 0) rt_post(ctx, dmix::kRtQuit, nullptr);
+    cudaStreamSynchronize(ctx->rt_stream);
+    ctx->rt_mb->alive = 0;
+    cudaGetLastError();
+}
+
+// One request through the mailbox; returns when the `out_words` words of its result are in `out`.
+int rt_request(doppler_b200_ctx* ctx, const MixArgs& a, int intype, int outtype, void* out, size_t out_words)
+{
+    if (ctx->rt_mb && ctx->rt_mb->alive != 0 && (a.in != ctx->rt_in_dev || a.tables != ctx->rt_tables_dev)) rt_quiesce(ctx);
+    if (!ctx->rt_mb || ctx->rt_mb->alive == 0) {
+        int rc = rt_start(ctx, a.in, a.tables, false);
+        if (rc) return rc;
+    }
+    const uint32_t seq = rt_post(ctx, dmix::rt_head(intype, outtype, a.npieces), &a);
     ctx->rt_requests++;
-    for (uint32_t spins = 1; mb->served != seq; spins++) {
+    unsigned char* dst = static_cast<unsigned char*>(out);
+    size_t got = 0;
+    for (uint32_t spins = 1;; spins++) {
+        const size_t now = dcollect::collect(ctx->rt_out, seq, dst, got, out_words);
+        if (now == out_words) break;
+        if (now != got) spins = 1;
+        got = now;
 #if defined(__x86_64__)
         __builtin_ia32_pause();
 #endif
-        if ((spins & 0x3fffu) == 0) {   // every ~100 us: did the kernel leave (idle time-out racing this request) or die?
+        if ((spins & 0x3fffu) == 0) {   // nothing new for ~100 us: did the kernel leave (idle time-out racing this request) or die?
             const cudaError_t q = cudaStreamQuery(ctx->rt_stream);
             if (q != cudaSuccess && q != cudaErrorNotReady) return fail(ctx, DOPPLER_B200_ECUDA, "resident kernel failed: %s", cudaGetErrorString(q));
-            if (q == cudaSuccess && mb->served != seq) {
-                int rc = rt_start(ctx);
+            if (q == cudaSuccess && dcollect::collect(ctx->rt_out, seq, dst, got, out_words) != out_words) {
+                // gone without having seen the request (a kernel that saw it serves it before it leaves)
+                int rc = rt_start(ctx, a.in, a.tables, true);
                 if (rc) return rc;
             }
         }
@@ -983,6 +1028,40 @@ int tiny_host_call(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int
     if (!(probe && alias_ok(in, &src_dev))) memcpy(sl.h_in, in, nsamples * ibps);
     if (probe && alias_ok(out, &dst_dev)) dst = out;
     const auto t_1 = std::chrono::steady_clock::now();
+    const bool rt_try = ctx->rt_idle_us != 0 && !probe;
+    if (rt_try && ctx->rt_steady.valid && (nblocks <= 1 || block_samples == 0)) {
+        // Steady state of a block stream (the reference's pump, main.rs:62-99): the same ratio as the last block and samplenum
+        // inside its period.  The planner's rule for that state (plan.cpp, Planner::plan: one periodic piece, base =
+        // samplenum - 1, samplenum' = (samplenum - 1 + n) mod P + 1) is applied here directly, with the table, period and
+        // division constants the last block's plan carried.
+        const float r = dplan::ratio(shifts[0], samplerate);
+        uint32_t r_bits;
+        memcpy(&r_bits, &r, 4);
+        const DevPiece& last = ctx->rt_steady.piece;
+        const uint32_t sn = *samplenum;
+        if (r_bits == ctx->rt_steady.r_bits && sn >= 1 && sn <= last.period) {
+            MixArgs a;
+            memset(&a, 0, sizeof a);
+            a.in = src_dev;
+            a.tables = ctx->arena;
+            a.nsamples = (uint32_t)nsamples;
+            a.npieces = 1;
+            a.inl[0] = last;
+            a.inl[0].k_begin = 0;
+            a.inl[0].k_end = (uint32_t)nsamples;
+            a.inl[0].base = sn - 1u;
+            const auto t_2r = std::chrono::steady_clock::now();
+            rc = rt_request(ctx, a, intype, outtype, out, nsamples * obps / 4);
+            if (rc) return rc;
+            *samplenum = (uint32_t)(((uint64_t)(sn - 1u) + nsamples) % last.period) + 1u;
+            if (ctx->trace && ctx->rt_requests > 64) {
+                auto ns = [](auto a, auto b) { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+                ctx->rt_steady_traced++;
+                ctx->rt_steady_ns[0] += ns(t_0, t_1), ctx->rt_steady_ns[1] += ns(t_1, t_2r), ctx->rt_steady_ns[2] += ns(t_2r, std::chrono::steady_clock::now());
+            }
+            return DOPPLER_B200_OK;
+        }
+    }
     std::vector<dplan::Run> runs;
     if (nblocks <= 1 || block_samples == 0)
         runs.push_back(dplan::Run{nsamples, dplan::ratio(shifts[0], samplerate)});
@@ -993,7 +1072,6 @@ int tiny_host_call(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int
     // staged blocks (the reference's 8192-byte pump block) go to the resident kernel when their plan fits its mailbox
     MixArgs rt_args;
     bool rt_filled = false;
-    const bool rt_try = ctx->rt_idle_us != 0 && !probe;
     const uint64_t launches_before = ctx->launches;
     rc = launch_mix(ctx, src_dev, dst_dev, nsamples, intype, outtype, runs, samplenum, sl.stream, &done, rt_try ? &rt_args : nullptr, &rt_filled);
     if (rc) return rc;
@@ -1005,16 +1083,19 @@ int tiny_host_call(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int
             ctx->tables_event_valid = false;
         }
         const auto t_2r = std::chrono::steady_clock::now();
-        rc = rt_request(ctx, rt_args, intype, outtype);
+        rc = rt_request(ctx, rt_args, intype, outtype, out, nsamples * obps / 4);   // (collects the result straight into `out`)
         if (rc) return rc;
+        ctx->rt_steady.valid = !ctx->rt_steady.off && runs.size() == 1 && rt_args.npieces == 1 && rt_args.inl[0].period != 0;
+        if (ctx->rt_steady.valid) {
+            ctx->rt_steady.piece = rt_args.inl[0];
+            memcpy(&ctx->rt_steady.r_bits, &rt_args.inl[0].r, 4);
+        }
         const auto t_3r = std::chrono::steady_clock::now();
-        memcpy(out, dst, nsamples * obps);
         if (ctx->trace) {
-            const auto t_4r = std::chrono::steady_clock::now();
             auto ns = [](auto a, auto b) { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
             if (ctx->rt_requests > 64) {   // (the first calls start the kernel, build tables, allocate: not the steady state)
                 ctx->rt_traced++;
-                ctx->rt_ns[0] += ns(t_0, t_1), ctx->rt_ns[1] += ns(t_1, t_2r), ctx->rt_ns[2] += ns(t_2r, t_3r), ctx->rt_ns[3] += ns(t_3r, t_4r);
+                ctx->rt_ns[0] += ns(t_0, t_1), ctx->rt_ns[1] += ns(t_1, t_2r), ctx->rt_ns[2] += ns(t_2r, t_3r);
             }
         }
         return DOPPLER_B200_OK;
@@ -1204,6 +1285,7 @@ int doppler_b200_create(int device, doppler_b200_ctx** ctx_out)
     if (const char* e = getenv("DOPPLER_B200_SMALL_MAX")) ctx->small_max = (uint32_t)strtoul(e, nullptr, 10);   // tuning knobs (tools/tune)
     if (const char* e = getenv("DOPPLER_B200_TINY_BYTES")) ctx->tiny_host_bytes = (size_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("DOPPLER_B200_RESIDENT_IDLE_US")) ctx->rt_idle_us = strtoull(e, nullptr, 10);
+    if (const char* e = getenv("DOPPLER_B200_NO_STEADY_RULE")) ctx->rt_steady.off = atoi(e) != 0;
     cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&ctx->meta_stream, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->tables_ready, cudaEventDisableTiming);
@@ -1226,9 +1308,13 @@ void doppler_b200_destroy(doppler_b200_ctx* ctx)
                 (unsigned long long)ctx->tiny_calls, (double)ctx->tiny_ns[0] / ctx->tiny_calls, (double)ctx->tiny_ns[1] / ctx->tiny_calls,
                 (double)ctx->tiny_ns[2] / ctx->tiny_calls, (double)ctx->tiny_ns[3] / ctx->tiny_calls);
     if (ctx->trace && ctx->rt_traced)
-        fprintf(stderr, "{\"resident_kernel_calls\": %llu, \"kernel_starts\": %llu, \"ns_per_call_after_the_first_64\": {\"stage_in\": %.0f, \"plan\": %.0f, \"request_to_served\": %.0f, \"copy_out\": %.0f}}\n",
+        fprintf(stderr, "{\"resident_kernel_calls\": %llu, \"kernel_starts\": %llu, \"ns_per_call_after_the_first_64\": {\"stage_in\": %.0f, \"plan\": %.0f, \"request_to_collected\": %.0f}}\n",
                 (unsigned long long)ctx->rt_requests, (unsigned long long)ctx->rt_starts, (double)ctx->rt_ns[0] / ctx->rt_traced,
-                (double)ctx->rt_ns[1] / ctx->rt_traced, (double)ctx->rt_ns[2] / ctx->rt_traced, (double)ctx->rt_ns[3] / ctx->rt_traced);
+                (double)ctx->rt_ns[1] / ctx->rt_traced, (double)ctx->rt_ns[2] / ctx->rt_traced);
+    if (ctx->trace && ctx->rt_steady_traced)
+        fprintf(stderr, "{\"resident_kernel_calls_planned_by_the_steady_state_rule\": %llu, \"ns_per_call\": {\"stage_in\": %.0f, \"plan\": %.0f, \"request_to_collected\": %.0f}}\n",
+                (unsigned long long)ctx->rt_steady_traced, (double)ctx->rt_steady_ns[0] / ctx->rt_steady_traced,
+                (double)ctx->rt_steady_ns[1] / ctx->rt_steady_traced, (double)ctx->rt_steady_ns[2] / ctx->rt_steady_traced);
     cudaSetDevice(ctx->device);
     rt_quiesce(ctx);
     cudaDeviceSynchronize();

@@ -24,6 +24,7 @@
 // f32->f32 16 (table / piece traffic is O(period) and excluded).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "sincosf_glibc.h"
@@ -1443,8 +1444,22 @@ struct SmallDone {
 // COHERENT (the resident kernel below, which outlives many calls): input is read with ld.global.cv and tables with
 // ld.global.cg, so that neither a previous call's block in the same host buffer nor a neighbouring table built after the
 // kernel started can be served from this SM's L1.
+// 16 bytes of flagged units: {w0, flag, w1, flag}.  Each 8-byte half is delivered whole (what NCCL's LL protocol rests on).
+__device__ __forceinline__ void store_units2(void* units, uint32_t first_unit, uint32_t w0, uint32_t w1, uint32_t flag)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<uint2*>(units) + first_unit), "r"(w0), "r"(flag), "r"(w1),
+                 "r"(flag)
+                 : "memory");
+}
+__device__ __forceinline__ void store_unit(void* units, uint32_t unit, uint32_t w, uint32_t flag)
+{
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(units) + unit), "r"(w), "r"(flag) : "memory");
+}
+
+// COHERENT also changes where the result goes: a.out is an array of 8-byte UNITS, unit u = {word u of the result, `flag`}
+// (the resident kernel's fence-free hand-over: the host takes a word when its flag shows the request number).
 template <int IN, int OUT, int V, bool COHERENT>
-__device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint32_t nctas)
+__device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint32_t nctas, uint32_t flag = 0)
 {
     constexpr int G = group_samples(IN, OUT);
     constexpr uint32_t kStep = kSmallThreads * V;
@@ -1508,7 +1523,17 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
                     res[i] = cmul_unfused(smp[i], phasor(q.r, piece_samplenum(q, k - q.k_begin)));
                 }
             }
-            if constexpr (OUT == I16 && G == 4) {
+            if constexpr (COHERENT) {
+                if constexpr (OUT == I16 && G == 4) {
+                    store_units2(a.out, 4u * g, egress_i16(res[0]), egress_i16(res[1]), flag);
+                    store_units2(a.out, 4u * g + 2u, egress_i16(res[2]), egress_i16(res[3]), flag);
+                } else if constexpr (OUT == I16) {
+                    store_units2(a.out, 2u * g, egress_i16(res[0]), egress_i16(res[1]), flag);
+                } else {
+                    store_units2(a.out, 4u * g, __float_as_uint(res[0].x), __float_as_uint(res[0].y), flag);
+                    store_units2(a.out, 4u * g + 2u, __float_as_uint(res[1].x), __float_as_uint(res[1].y), flag);
+                }
+            } else if constexpr (OUT == I16 && G == 4) {
                 __stcs(reinterpret_cast<uint4*>(a.out) + g, make_uint4(egress_i16(res[0]), egress_i16(res[1]), egress_i16(res[2]), egress_i16(res[3])));
             } else if constexpr (OUT == I16) {
                 __stcs(reinterpret_cast<uint2*>(a.out) + g, make_uint2(egress_i16(res[0]), egress_i16(res[1])));
@@ -1531,7 +1556,13 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
         } else {
             smp = load_sample<IN>(a.in, tail);
         }
-        store_sample<OUT>(a.out, tail, cmul_unfused(smp, phasor(q.r, piece_samplenum(q, tail - q.k_begin))));
+        const float2 res = cmul_unfused(smp, phasor(q.r, piece_samplenum(q, tail - q.k_begin)));
+        if constexpr (!COHERENT)
+            store_sample<OUT>(a.out, tail, res);
+        else if constexpr (OUT == I16)
+            store_unit(a.out, tail, egress_i16(res), flag);
+        else
+            store_units2(a.out, 2u * tail, __float_as_uint(res.x), __float_as_uint(res.y), flag);
     }
 }
 
@@ -1560,45 +1591,48 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
 // The reference calls its mixer once per 8192-byte pump block (main.rs:49,70), and a realtime stream delivers such a block
 // every few milliseconds.  Even the zero-copy small launch above spends most of its ~14 us in the launch itself (driver call,
 // launch latency, kernel start-up).  So the first per-block call starts ONE CTA that stays on the chip and serves the following
-// blocks from a mailbox in mapped pinned host memory:
-//     host:   copy the block into the pinned staging buffer, plan it, write request n (types + MixArgs) into the mailbox
-//     device: the CTA reads the mailbox in one wave per look; on a new request it mixes the block straight from / to host
-//             memory, fences system-wide and writes served = n
-//     host:   spins on served (its own memory), copies the result out
-// Two PCIe round trips (request, block) and one posted write per block instead of a kernel launch.  The kernel leaves by itself after
-// `idle_ns` without a request (alive = 0, after one last look at seq), and at once when the host sets quit; the host starts
-// another when it finds alive == 0.  Only launches whose pieces fit MixArgs::inl come here.
-// Mailbox layout.  Every round trip over PCIe costs ~2 us, so a request must be visible to the device in ONE read: the request
-// (types + MixArgs + a checksum) travels in 64-byte lines whose last word is the request number.  The sixteen lanes that read
-// a line do so in one warp instruction, a read of a cache line returns a coherent snapshot, and the host writes a line's payload
-// before its tag (x86 stores are ordered) -- so a line whose tag is n carries request n, and the CTA reads all lines in one wave
-// and takes the request when every tag shows the same new number.  Nothing promises that the memory system fetches a line in
-// ONE request rather than as two 32-byte sectors at different times (the first of which could then predate the host's write
-// while the second shows the new tag), so the payload also carries the sum of its words: a wave that mixes words of two
-// requests is rejected unless the mixed words are equal anyway, and simply looked at again.  (One tag per 32-byte sector needs
-// no such argument, but doubles the read requests of a wave: 10.1 us per block against 8.2-9.5 interleaved on one box, no
-// difference on a slower one; DOPPLER_RT_SECTOR_TAGS builds it.)
-constexpr int kRtPayloadWords = 3 + (int)(sizeof(MixArgs) / 4);   // intype, outtype, MixArgs, checksum (last)
-#ifdef DOPPLER_RT_SECTOR_TAGS   // A/B build: one tag per 32-byte sector
-constexpr int kRtUnit = 8;
-#else
-constexpr int kRtUnit = 16;                                         // words per tagged unit: a 64-byte line
-#endif
-constexpr int kRtSectors = (kRtPayloadWords + kRtUnit - 2) / (kRtUnit - 1);
-struct RtSector {
-    uint32_t w[kRtUnit - 1];
+// blocks, everything travelling through mapped pinned host memory:
+//     host:   copy the block into the pinned staging buffer, plan it, write request n into the mailbox
+//     device: warp 0 looks at the mailbox (one 128-byte read per look); on a new request the CTA mixes the block from the
+//             staging buffer and writes every 32-bit word of the result next to the request number
+//     host:   collects the result: a word is there when its neighbour shows n
+// What a block costs is PCIe round trips (~2 us each), so the protocol is built to need few of them:
+//   * A request is TWO 64-byte lines whose last word is the request number: head word (types, number of pieces), sample count,
+//     up to kRtPieces pieces of 8 words, the sum of those words.  The buffers' addresses travel with the launch, not with the
+//     request.  The host writes a line's payload before its tag (x86 stores are ordered), a read of a line returns a coherent
+//     snapshot, and the CTA takes the request when both tags show the same new number and the words add up -- the sum covers
+//     what nothing promises, that a line is fetched in one piece rather than as two 32-byte sectors at different times.
+//   * One look at a time, by warp 0 alone while the other warps wait at a barrier.  (Keeping four looks in flight, issued a
+//     fraction of a microsecond apart so that a request need not wait for the previous look to return, was measured and LOST
+//     3.4 us per block: reads of host memory still in flight delay the block's own reads.  With blocks sent back to back the
+//     first look after a block always comes too early -- the result is still on its way to the host -- and costs a round trip;
+//     delaying it by 1.2 us gained 0.2 us per block, by less it lost up to 0.5: not kept.  profiles/r02_percall_mailbox_ab.txt)
+//   * The result needs no fence and no completion flag.  An 8-byte store is delivered whole, so the unit {word, n} is its own
+//     completion signal (the scheme of NCCL's LL protocol, which runs over PCIe for the same reason); a system-scope fence before
+//     a flag costs a round trip of ~3 us on top of the 16 KB this writes instead of 8.
+// The kernel leaves by itself after `idle_ns` without a request (alive = 0, then one last look issued after that), and at once
+// on a quit request; the host starts another when it finds alive == 0.  Only plans of up to kRtPieces pieces come here.
+constexpr int kRtPieces = 3;
+constexpr int kRtPieceWords = 8;                                     // DevPiece up to and including `shift` (small_body reads no more)
+constexpr int kRtPayloadWords = 2 + kRtPieces * kRtPieceWords + 1;   // head, nsamples, pieces, checksum (last)
+constexpr int kRtLines = 2;
+constexpr uint32_t kRtQuit = 0x80000000u;                            // head word: leave now
+constexpr uint32_t kRtLast = 0x40000000u;                            // (device only) this request came with the last look
+struct RtLine {
+    uint32_t w[15];
     uint32_t tag;
 };
 struct RtMailbox {
-    RtSector req[kRtSectors];   // host -> device
-    volatile uint32_t quit;     // host -> device: leave now                                           (its own cache line)
-    uint32_t pad0[15];
-    volatile uint32_t served;   // device -> host: latest request whose output is visible to the host   (its own cache line)
+    RtLine req[kRtLines];       // host -> device
     volatile uint32_t alive;    // generation of the resident kernel (the host writes it before the launch); the kernel clears it when it leaves
-    uint32_t pad1[14];
+    uint32_t pad[15];
 };
-static_assert(sizeof(RtSector) == 4 * kRtUnit && sizeof(MixArgs) % 4 == 0, "mailbox lines");
-static_assert(kRtSectors * kRtUnit + 1 <= kSmallThreads, "one mailbox word per thread");
+static_assert(sizeof(RtLine) == 64 && kRtLines * 16 == 32, "the mailbox is one warp-wide read");
+static_assert(kRtPayloadWords <= kRtLines * 15, "the request fits its lines");
+static_assert(kRtPieces <= kInlinePieces && kRtPieceWords * 4 <= (int)offsetof(DevPiece, step_u), "pieces travel up to `shift`");
+
+// head word of a request
+__host__ __device__ constexpr uint32_t rt_head(int intype, int outtype, uint32_t npieces) { return (uint32_t)outtype | ((uint32_t)intype << 1) | (npieces << 2); }
 
 __device__ __forceinline__ uint64_t global_timer_ns()
 {
@@ -1607,75 +1641,95 @@ __device__ __forceinline__ uint64_t global_timer_ns()
     return t;
 }
 
-static __global__ void __launch_bounds__(kSmallThreads, 1) mix_resident_kernel(RtMailbox* mb, uint64_t idle_ns, uint32_t gen)
+// One look's verdict, computed by the whole warp from the word each lane read: the request number if the lines hold one whole
+// request other than `last`, else `last`.
+__device__ __forceinline__ uint32_t rt_verdict(uint32_t v, uint32_t lane, uint32_t last)
 {
-    __shared__ __align__(16) uint32_t s_words[kRtSectors * (kRtUnit - 1) + 2];   // the request's payload: intype, outtype, MixArgs
-    __shared__ uint32_t s_tag[kRtSectors];
-    __shared__ int s_part[kSmallThreads / 32];
-    __shared__ uint32_t s_quit, s_idle;
+    const uint32_t tag0 = __shfl_sync(0xffffffffu, v, 15), tag1 = __shfl_sync(0xffffffffu, v, 31);
+    const uint32_t w = (lane >> 4) * 15u + (lane & 15u);   // payload index of this lane's word (tags aside)
+    int contrib = 0;
+    if ((lane & 15u) != 15u) {
+        if (w < (uint32_t)kRtPayloadWords - 1u)
+            contrib = (int)v;
+        else if (w == (uint32_t)kRtPayloadWords - 1u)
+            contrib = -(int)v;
+    }
+    const int total = __reduce_add_sync(0xffffffffu, contrib);
+    return (tag0 == tag1 && total == 0) ? tag0 : last;
+}
+
+static __global__ void __launch_bounds__(kSmallThreads, 1)
+mix_resident_kernel(RtMailbox* mb, const void* in, void* out_units, const float2* tables, uint64_t idle_ns, uint32_t gen, uint32_t last)
+{
+    __shared__ MixArgs s_args;
+    __shared__ uint32_t s_head, s_seq;
     const uint32_t tid = threadIdx.x;
     const volatile uint32_t* words = reinterpret_cast<const volatile uint32_t*>(mb);
-    uint32_t last = mb->served;   // (the same value in every thread; written by the previous resident kernel or the host)
-    uint64_t t0 = global_timer_ns();
-    bool last_look = false;
+    for (uint32_t i = tid; i < sizeof(MixArgs) / 4; i += kSmallThreads) reinterpret_cast<uint32_t*>(&s_args)[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        s_args.in = in;
+        s_args.out = out_units;
+        s_args.tables = tables;
+        s_args.smem_piece = 0xffffffffu;
+        s_args.max_claim = 1;
+    }
     for (;;) {
-        // one wave over the mailbox: thread t reads word t of the request lines, thread kRtSectors*kRtUnit the quit word
-        int contrib = 0;   // payload words add up to the checksum word
-        if (tid < (uint32_t)(kRtSectors * kRtUnit)) {
-            const uint32_t v = words[tid];
-            const uint32_t w = (tid / kRtUnit) * (kRtUnit - 1) + tid % kRtUnit;   // payload index (of the words that are not tags)
-            if (tid % kRtUnit == kRtUnit - 1) {
-                s_tag[tid / kRtUnit] = v;
-            } else {
-                s_words[w] = v;
-                if (w < (uint32_t)kRtPayloadWords - 1u)
-                    contrib = (int)v;
-                else if (w == (uint32_t)kRtPayloadWords - 1u)
-                    contrib = -(int)v;
+        if (tid < 32u) {
+            // warp 0 looks for the next request; the other warps wait at the barrier below
+            uint32_t v = 0, seq = last;
+            bool leave = false;
+            const uint64_t t0 = global_timer_ns();
+            for (;;) {   // one look at a time (see above)
+                v = words[tid];
+                seq = rt_verdict(v, tid, last);
+                if (seq != last) break;
+                if (__shfl_sync(0xffffffffu, global_timer_ns() - t0 > idle_ns ? 1 : 0, 0)) {   // (lane 0's clock: one verdict for the warp)
+                    leave = true;
+                    break;
+                }
             }
-        } else if (tid == (uint32_t)(kRtSectors * kRtUnit)) {
-            s_quit = mb->quit;
-            s_idle = global_timer_ns() - t0 > idle_ns ? 1u : 0u;
+            if (leave) {
+                // idle: announce the departure, then look once more -- a request that raced with the time-out is still served
+                if (tid == 0) {
+                    if (mb->alive == gen) mb->alive = 0;
+                    __threadfence_system();
+                }
+                __syncwarp();
+                v = words[tid];
+                seq = rt_verdict(v, tid, last);
+            }
+            if (seq != last) {
+                const uint32_t w = (tid >> 4) * 15u + (tid & 15u);
+                if ((tid & 15u) != 15u) {
+                    if (w == 0) {
+                        s_head = leave ? (v | kRtLast) : v;
+                        s_seq = seq;
+                        s_args.npieces = (v >> 2) & 7u;
+                    } else if (w == 1) {
+                        s_args.nsamples = v;
+                    } else if (w < (uint32_t)kRtPayloadWords - 1u) {
+                        const uint32_t pw = w - 2u;
+                        reinterpret_cast<uint32_t*>(&s_args.inl[pw / kRtPieceWords])[pw % kRtPieceWords] = v;
+                    }
+                }
+            } else if (tid == 0) {
+                s_head = kRtQuit;   // nothing came with the last look
+                s_seq = last;
+            }
         }
-        const int wsum = __reduce_add_sync(0xffffffffu, contrib);
-        if ((tid & 31u) == 0) s_part[tid >> 5] = wsum;
         __syncthreads();
-        const uint32_t seq = s_tag[0];
-        bool whole = true;
-#pragma unroll
-        for (int i = 1; i < kRtSectors; i++) whole = whole && s_tag[i] == seq;
-        int total = 0;
-#pragma unroll
-        for (int i = 0; i < kSmallThreads / 32; i++) total += s_part[i];
-#ifdef DOPPLER_RT_NO_CHECKSUM   // A/B build
-        total = 0;
-#endif
-        const bool fresh = whole && seq != last && total == 0;
-        const bool quit = s_quit != 0, idle = s_idle != 0;
-        if (fresh) {
-            const MixArgs& sa = *reinterpret_cast<const MixArgs*>(s_words + 2);   // (8-byte aligned: s_words is 16-byte aligned)
-            switch ((s_words[0] << 1) | s_words[1]) {
-            case 0: small_body<I16, I16, 4, true>(sa, 0, 1); break;
-            case 1: small_body<I16, F32, 4, true>(sa, 0, 1); break;
-            case 2: small_body<F32, I16, 4, true>(sa, 0, 1); break;
-            default: small_body<F32, F32, 4, true>(sa, 0, 1); break;
-            }
-            __threadfence_system();   // this thread's stores into host memory are visible before `served` can be
-            __syncthreads();
-            if (tid == 0) mb->served = seq;
-            last = seq;
-            t0 = global_timer_ns();
+        const uint32_t head = s_head;
+        if (head & kRtQuit) break;
+        last = s_seq;
+        switch (head & 3u) {
+        case 0: small_body<I16, I16, 4, true>(s_args, 0, 1, last); break;
+        case 1: small_body<I16, F32, 4, true>(s_args, 0, 1, last); break;
+        case 2: small_body<F32, I16, 4, true>(s_args, 0, 1, last); break;
+        default: small_body<F32, F32, 4, true>(s_args, 0, 1, last); break;
         }
-        if (last_look || quit) break;
-        if (!fresh && idle) {
-            // idle: announce the departure, then look once more -- a request that raced with the time-out is still served
-            if (tid == 0) {
-                if (mb->alive == gen) mb->alive = 0;
-                __threadfence_system();
-            }
-            last_look = true;
-        }
-        __syncthreads();   // s_words / s_tag are rewritten next round
+        if (head & kRtLast) break;   // (served after the departure was announced: the host will start a successor)
+        __syncthreads();             // s_args / s_head are rewritten by the next request
     }
     if (tid == 0) {
         if (mb->alive == gen) mb->alive = 0;   // (a successor the host has already announced keeps its own mark)

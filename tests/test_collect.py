@@ -1,0 +1,83 @@
+"""Host side of the resident kernel's fence-free hand-over (doppler_b200/csrc/collect.cpp): the device writes its result as
+8-byte units {word, request number}; the host takes a word when its neighbour shows the number.  CPU-only: the units are
+written here, in the orders a device may deliver them."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    L = ctypes.CDLL(os.path.join(ROOT, "tests", "native", "libhostcheck.so"))
+    for f in (L.hostcheck_collect, L.hostcheck_collect_scalar):
+        f.restype = ctypes.c_size_t
+        f.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t]
+    return L
+
+
+def _units(words, flags):
+    u = np.empty(2 * words.size, np.uint32)
+    u[0::2] = words
+    u[1::2] = flags
+    return u
+
+
+@pytest.mark.parametrize("which", ["hostcheck_collect", "hostcheck_collect_scalar"])
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 63, 64, 2048, 2049, 16383])
+@pytest.mark.parametrize("misalign", [0, 1, 2])
+def test_complete_result_is_copied_out(lib, which, n, misalign):
+    rng = np.random.default_rng(n)
+    words = rng.integers(0, 2**32, n, dtype=np.uint32)
+    u = _units(words, np.full(n, 77, np.uint32))
+    raw = np.full(4 * n + 16, 0xAB, np.uint8)   # the caller's buffer: any alignment, nothing written beyond the result
+    out = raw[misalign:]
+    got = getattr(lib, which)(u.ctypes.data, 77, out.ctypes.data, 0, n)
+    assert got == n
+    assert np.array_equal(out[:4 * n].view(np.uint8), words.view(np.uint8))
+    assert np.all(raw[misalign + 4 * n:] == 0xAB) and np.all(raw[:misalign] == 0xAB)
+
+
+@pytest.mark.parametrize("which", ["hostcheck_collect", "hostcheck_collect_scalar"])
+def test_stops_at_the_first_missing_word_and_resumes(lib, which):
+    n = 2048
+    rng = np.random.default_rng(1)
+    words = rng.integers(0, 2**32, n, dtype=np.uint32)
+    stale = rng.integers(0, 2**32, n, dtype=np.uint32)
+    fn = getattr(lib, which)
+    for hole in [0, 1, 5, 8, 15, 16, 1000, 2040, 2047]:
+        flags = np.full(n, 9, np.uint32)
+        flags[hole] = 8                           # the previous request's unit is still there
+        data = words.copy()
+        data[hole] = stale[hole]
+        u = _units(data, flags)
+        out = np.zeros(n, np.uint32)
+        got = fn(u.ctypes.data, 9, out.ctypes.data, 0, n)
+        assert got <= hole and hole - got < 8      # (the vector path works in lines of eight units)
+        assert np.array_equal(out[:got], words[:got])
+        u[2 * hole], u[2 * hole + 1] = words[hole], 9   # it arrives
+        assert fn(u.ctypes.data, 9, out.ctypes.data, got, n) == n
+        assert np.array_equal(out, words)
+
+
+def test_units_arriving_in_any_order(lib):
+    """Units land in arbitrary order; the collector never hands out a word whose flag is not the request's."""
+    n = 1000
+    rng = np.random.default_rng(2)
+    old = rng.integers(0, 2**32, n, dtype=np.uint32)
+    new = rng.integers(0, 2**32, n, dtype=np.uint32)
+    u = _units(old, np.full(n, 41, np.uint32))
+    out = np.zeros(n, np.uint32)
+    got = 0
+    order = rng.permutation(n)
+    for step, k in enumerate(order):
+        u[2 * k], u[2 * k + 1] = new[k], 42
+        if step % 37 == 0 or step == n - 1:
+            now = lib.hostcheck_collect(u.ctypes.data, 42, out.ctypes.data, got, n)
+            assert now >= got
+            assert np.array_equal(out[:now], new[:now])
+            got = now
+    assert got == n

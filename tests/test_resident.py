@@ -111,3 +111,55 @@ def test_context_ends_while_the_kernel_is_resident(oracle):
         t0 = time.perf_counter()
         m.close()
         assert time.perf_counter() - t0 < 1.0
+
+
+@pytest.mark.parametrize("intype,outtype", [(I16, I16), (I16, F32), (F32, I16), (F32, F32)])
+def test_every_block_size_through_the_same_units(oracle, fresh, intype, outtype):
+    """The result comes back as flagged 8-byte units in ONE buffer reused by every block (collect.cpp): shrinking, growing and
+    ragged block sizes (group tails of 1..3 samples, the 32 KiB limit of the path and the first size beyond it) must never
+    pick up a unit of an earlier block."""
+    rng = np.random.default_rng(21 + 2 * intype + outtype)
+    top = (32 << 10) // BPS[intype]                              # largest block the resident kernel serves
+    sizes = list(range(1, 41)) + [2047, 2048, 2049, top - 1, top, top + 1, 3, top, 1, 2048, 5, top - 3, 2]
+    sn_g = sn_o = 123
+    before = fresh.launch_count
+    for n in sizes:
+        buf = make_input(rng, n, intype)
+        got, sn_g = fresh.mix(buf, intype, outtype, -4321.5, 1_024_000, samplenum=sn_g)
+        want, sn_o = oracle.mix(buf, intype, outtype, -4321.5, 1_024_000, samplenum=sn_o)
+        assert sn_g == sn_o and same(got, want, outtype), n
+    assert fresh.launch_count - before <= 8                      # (two blocks above the limit, the resident kernel, a table or two)
+
+
+def test_identical_blocks_back_to_back(oracle, fresh):
+    """The same bytes in and (with a table, P = 256 dividing the block) the same bytes out, block after block: only the request
+    number in the units tells a new result from the previous one."""
+    rng = np.random.default_rng(31)
+    buf = make_input(rng, 2048, I16)
+    sn_g = sn_o = 0
+    for b in range(40):
+        got, sn_g = fresh.mix(buf, I16, I16, -15000.0, 256000, samplenum=sn_g)
+        want, sn_o = oracle.mix(buf, I16, I16, -15000.0, 256000, samplenum=sn_o)
+        assert sn_g == sn_o and np.array_equal(got, want), b
+
+
+def test_plans_beyond_the_request_lines_keep_the_launch(oracle, fresh):
+    """A request carries at most three pieces; a small call with more (one shift per 256 bytes of input) is an ordinary launch,
+    and the resident kernel serves the blocks around it."""
+    rng = np.random.default_rng(41)
+    fs = 1_024_000
+    sn_g = sn_o = 0
+    for b in range(12):
+        buf = make_input(rng, 2048, I16)
+        if b % 3 == 1:
+            shifts = rng.uniform(-9000, 9000, 32).astype(np.float32)
+            got, sn_g = fresh.mix_blocks(buf, I16, F32, shifts, fs, samplenum=sn_g, block_bytes=256)
+            parts = []
+            for i, s in enumerate(shifts):                        # the same thing as 32 chained calls of the reference's mixer
+                part, sn_o = oracle.mix(buf[256 * i:256 * (i + 1)], I16, F32, float(s), fs, samplenum=sn_o)
+                parts.append(part)
+            want = np.concatenate(parts)
+        else:
+            got, sn_g = fresh.mix(buf, I16, F32, 2500.0 * b, fs, samplenum=sn_g)
+            want, sn_o = oracle.mix(buf, I16, F32, 2500.0 * b, fs, samplenum=sn_o)
+        assert sn_g == sn_o and same_bits_f32(got, want), b

@@ -2,6 +2,7 @@
 // (one 8192-byte block per call, src/main.rs:49,70) and at the batched sizes INTEGRATION.md recommends,
 // with the resident kernel (default), with a zero-copy launch per block, and with the staged pipeline; pageable and pinned caller buffers.
 // Build: make -C tools/tune percall      Run (GPU box): tools/tune/percall
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -58,6 +59,38 @@ int main()
                     free(out);
                 }
             }
+    }
+    // Paced: a realtime stream delivers one block every few milliseconds, not back to back.  Calls 30-60 us apart (the
+    // resident kernel stays; a random phase against its looks), the call's own duration timed -- mean and median.
+    for (int mode = 2; mode >= 1; mode--) {
+        doppler_b200_tune(ctx, DOPPLER_B200_TUNE_TINY_HOST_BYTES, 128u << 10);
+        doppler_b200_tune(ctx, DOPPLER_B200_TUNE_RESIDENT_IDLE_US, mode == 2 ? 20000 : 0);
+        const size_t n = 2048, bytes = n * 4;
+        void *in = malloc(bytes), *out = malloc(bytes);
+        memset(in, 1, bytes);
+        uint32_t sn = 0, lcg = 12345;
+        size_t got = 0;
+        const int iters = quick ? 3000 : 10000;
+        std::vector<double> us(iters);
+        for (int i = -50; i < iters; i++) {
+            lcg = lcg * 1664525u + 1013904223u;
+            const double gap_us = 30.0 + (lcg >> 8) * (30.0 / (1u << 24));
+            const auto g0 = now();
+            while (std::chrono::duration<double, std::micro>(now() - g0).count() < gap_us) {
+            }
+            const auto t0 = now();
+            if (doppler_b200_mix(ctx, in, bytes, DOPPLER_B200_I16, DOPPLER_B200_I16, 5000.0f, 1024000, &sn, out, bytes, &got) != 0) return 3;
+            if (i >= 0) us[i] = std::chrono::duration<double, std::micro>(now() - t0).count();
+        }
+        double mean = 0;
+        for (double u : us) mean += u / iters;
+        std::sort(us.begin(), us.end());
+        printf("{\"call\": \"doppler_b200_mix i16->i16\", \"path\": \"%s\", \"caller_buffers\": \"pageable\", \"samples_per_call\": %zu, "
+               "\"paced\": \"30-60 us between calls\", \"us_per_call\": %.2f, \"median_us\": %.2f, \"p99_us\": %.2f}\n",
+               mode == 2 ? "resident kernel / zero-copy" : "zero-copy launch per block", n, mean, us[iters / 2], us[iters * 99 / 100]);
+        fflush(stdout);
+        free(in);
+        free(out);
     }
     doppler_b200_destroy(ctx);
     return 0;
