@@ -1625,7 +1625,10 @@ struct RtLine {
 struct RtMailbox {
     RtLine req[kRtLines];       // host -> device
     volatile uint32_t alive;    // generation of the resident kernel (the host writes it before the launch); the kernel clears it when it leaves
-    uint32_t pad[15];
+    uint32_t pad0[15];
+    volatile uint32_t served;   // device -> its successor: the latest request taken (a kernel that starts behind one that was still
+                                // leaving must not take that one's last request again); the host never reads it (its own line)
+    uint32_t pad1[15];
 };
 static_assert(sizeof(RtLine) == 64 && kRtLines * 16 == 32, "the mailbox is one warp-wide read");
 static_assert(kRtPayloadWords <= kRtLines * 15, "the request fits its lines");
@@ -1665,6 +1668,10 @@ mix_resident_kernel(RtMailbox* mb, const void* in, void* out_units, const float2
     __shared__ uint32_t s_head, s_seq;
     const uint32_t tid = threadIdx.x;
     const volatile uint32_t* words = reinterpret_cast<const volatile uint32_t*>(mb);
+    {
+        const uint32_t s = mb->served;   // (written by a predecessor on the same stream: complete before this kernel started)
+        if (s != 0 && (int32_t)(s - last) > 0) last = s;
+    }
     for (uint32_t i = tid; i < sizeof(MixArgs) / 4; i += kSmallThreads) reinterpret_cast<uint32_t*>(&s_args)[i] = 0;
     __syncthreads();
     if (tid == 0) {
@@ -1722,6 +1729,7 @@ mix_resident_kernel(RtMailbox* mb, const void* in, void* out_units, const float2
         const uint32_t head = s_head;
         if (head & kRtQuit) break;
         last = s_seq;
+        if (tid == 0) mb->served = last;
         switch (head & 3u) {
         case 0: small_body<I16, I16, 4, true>(s_args, 0, 1, last); break;
         case 1: small_body<I16, F32, 4, true>(s_args, 0, 1, last); break;

@@ -163,3 +163,25 @@ def test_plans_beyond_the_request_lines_keep_the_launch(oracle, fresh):
             got, sn_g = fresh.mix(buf, I16, F32, 2500.0 * b, fs, samplenum=sn_g)
             want, sn_o = oracle.mix(buf, I16, F32, 2500.0 * b, fs, samplenum=sn_o)
         assert sn_g == sn_o and same_bits_f32(got, want), b
+
+
+def test_time_out_races(oracle, fresh):
+    """An idle time-out of the order of the gap between calls: the kernel leaves and returns hundreds of times, with requests
+    arriving before, during and after its last look (served by the leaving kernel, by a successor queued behind it, or by
+    one started when the host finds nobody there).  Every block exactly once, in order: bytes and samplenum chain as the oracle's."""
+    rng = np.random.default_rng(51)
+    fresh.tune(resident_idle_us=120)
+    fs = 1_024_000
+    sn_g = sn_o = 0
+    before = fresh.launch_count
+    for b in range(500):
+        n = 2048 if b % 5 else int(rng.integers(1, 2049))
+        buf = make_input(rng, n, I16)
+        shift = 5000.0 if b % 50 < 40 else float(rng.uniform(-9000, 9000))   # mostly the steady-state rule, some new ratios
+        t_end = time.perf_counter() + float(rng.uniform(0, 250e-6))
+        while time.perf_counter() < t_end:
+            pass
+        got, sn_g = fresh.mix(buf, I16, I16, shift, fs, samplenum=sn_g)
+        want, sn_o = oracle.mix(buf, I16, I16, shift, fs, samplenum=sn_o)
+        assert sn_g == sn_o and np.array_equal(got, want), b
+    assert fresh.launch_count - before >= 20    # (it did leave and return)
