@@ -594,6 +594,10 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
 
         const uint32_t nsamp = (uint32_t)(l1 - l0);
         const bool small = done != nullptr || nsamp <= ctx->small_max;   // latency-shaped kernel: no segments, no shared-memory table
+        // The persistent kernels are one CTA per SM with the whole register file, and the lean one deals its tiles out
+        // statically: next to a resident CTA of the per-block path (it lingers for its idle time-out after the last
+        // block) one of them would wait for a neighbour to finish -- up to twice the launch time.  It leaves first.
+        if (!small && ctx->rt_mb && ctx->rt_mb->alive != 0) rt_quiesce(ctx);
         std::vector<DevSeg> segs;
         uint32_t tail_begin = nsamp;
         if (!small)

@@ -185,3 +185,24 @@ def test_time_out_races(oracle, fresh):
         want, sn_o = oracle.mix(buf, I16, I16, shift, fs, samplenum=sn_o)
         assert sn_g == sn_o and np.array_equal(got, want), b
     assert fresh.launch_count - before >= 20    # (it did leave and return)
+
+
+def test_kernel_leaves_before_a_persistent_launch(oracle, fresh):
+    """The persistent kernels take one CTA per SM with the whole register file; the resident CTA would make one of them wait
+    for a neighbour (twice the launch time with the statically dealt lean kernel: tools/gpu/resident_coexist.py).  So a
+    launch above the small-kernel limit sends it away first, and the next block brings it back."""
+    rng = np.random.default_rng(61)
+    fresh.tune(resident_idle_us=5_000_000)
+    blk = make_input(rng, 2048, I16)
+    big = make_input(rng, 5_000_001, I16)
+    want_blk, _ = oracle.mix(blk, I16, I16, 5000.0, 1_024_000, samplenum=7)
+    want_big, _ = oracle.mix(big, I16, I16, -15000.0, 256000)
+    fresh.mix(blk, I16, I16, 5000.0, 1_024_000, samplenum=7)
+    before = fresh.launch_count
+    got, _ = fresh.mix(blk, I16, I16, 5000.0, 1_024_000, samplenum=7)
+    assert np.array_equal(got, want_blk) and fresh.launch_count == before          # served by the kernel on the chip
+    got, _ = fresh.mix(big, I16, I16, -15000.0, 256000)
+    assert np.array_equal(got, want_big)
+    mid = fresh.launch_count
+    got, _ = fresh.mix(blk, I16, I16, 5000.0, 1_024_000, samplenum=7)
+    assert np.array_equal(got, want_blk) and fresh.launch_count == mid + 1         # a new resident kernel
