@@ -8,3 +8,8 @@ for i in 1 2 3 4; do
   e=$(date +%s%N)
   echo "{\"run\": $i, \"wall_ms\": $(( (e-s)/1000000 )), \"stats\": [$(grep -E '^\{' /tmp/err.txt | paste -sd, -)]}"
 done
+# the floor: a process that does nothing but create a CUDA context (tools/tune/ctxtime.cu)
+for i in 1 2 3; do
+  s=$(date +%s%N); o=$(tools/tune/ctxtime); e=$(date +%s%N)
+  echo "{\"run\": $i, \"wall_ms\": $(( (e-s)/1000000 )), \"stats\": [$o]}"
+done
