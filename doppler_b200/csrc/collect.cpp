@@ -6,7 +6,24 @@
 #include <immintrin.h>
 #endif
 
+#include <atomic>
+
 namespace dcollect {
+
+void post(volatile uint32_t* mailbox, int sectors, uint32_t seq, const uint32_t* payload, int payload_words)
+{
+    constexpr int kW = 7;   // payload words per sector
+    for (int t = 0; t < sectors; t++) {
+        volatile uint32_t* sector = mailbox + 8 * t;
+        for (int i = 0; i < kW; i++) {
+            const int w = t * kW + i;
+            sector[i] = w < payload_words ? payload[w] : 0u;
+        }
+        std::atomic_thread_fence(std::memory_order_release);   // (x86 keeps stores in order; this keeps the compiler from moving them)
+        sector[kW] = seq;
+    }
+    std::atomic_thread_fence(std::memory_order_seq_cst);   // out of the store buffer now, not when the caller's spin loop lets it
+}
 
 #if defined(__x86_64__)
 __attribute__((target("avx2"))) static size_t collect_avx2(const uint32_t* units, uint32_t seq, unsigned char* out, size_t from, size_t n)

@@ -920,17 +920,12 @@ int rt_start(doppler_b200_ctx* ctx, const void* in_dev, const void* tables_dev, 
 // A request in the mailbox's tagged lines: payload first, then the line's tag (mixer_kernels.cuh: RtMailbox).
 static uint32_t rt_post(doppler_b200_ctx* ctx, uint32_t head, const MixArgs* a)
 {
-    constexpr int kW = 15;   // payload words per line
-    uint32_t payload[dmix::kRtLines * kW] = {0};
+    uint32_t payload[dmix::kRtPayloadWords] = {0};
     payload[0] = head;
     if (a) {
         payload[1] = a->nsamples;
         for (uint32_t p = 0; p < a->npieces; p++) memcpy(payload + 2 + p * dmix::kRtPieceWords, &a->inl[p], dmix::kRtPieceWords * 4);
     }
-    uint32_t sum = 0;
-    for (int i = 0; i < dmix::kRtPayloadWords - 1; i++) sum += payload[i];
-    payload[dmix::kRtPayloadWords - 1] = sum;
-    dmix::RtMailbox* mb = ctx->rt_mb;
     uint32_t seq = ++ctx->rt_seq;
     if (seq == 0) {
         // the numbers wrap: no unit may still carry one that is about to be used again (the kernel is idle: every request
@@ -938,13 +933,8 @@ static uint32_t rt_post(doppler_b200_ctx* ctx, uint32_t head, const MixArgs* a)
         memset(ctx->rt_out, 0, kRtOutUnits * 8);
         seq = ++ctx->rt_seq;   // (0 is the mailbox's initial state)
     }
-    for (int l = 0; l < dmix::kRtLines; l++) {
-        volatile uint32_t* line = mb->req[l].w;
-        for (int i = 0; i < kW; i++) line[i] = payload[l * kW + i];
-        std::atomic_thread_fence(std::memory_order_release);
-        *const_cast<volatile uint32_t*>(&mb->req[l].tag) = seq;
-    }
-    std::atomic_thread_fence(std::memory_order_seq_cst);   // (out of the store buffer now, not when the spin loop's loads let it)
+    static_assert(offsetof(dmix::RtMailbox, req) == 0 && sizeof(dmix::RtSector) == 32, "the request sectors lead the mailbox");
+    dcollect::post(reinterpret_cast<volatile uint32_t*>(ctx->rt_mb), dmix::kRtSectors, seq, payload, dmix::kRtPayloadWords);
     return seq;
 }
 

@@ -1470,6 +1470,24 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
     // unevenly spread: 2.06 steps per CTA means a third of the CTAs run 3 while the rest wait)
     const uint32_t g_begin = (uint32_t)((uint64_t)ngroups * cta / nctas);
     const uint32_t g_end = (uint32_t)((uint64_t)ngroups * (cta + 1) / nctas);
+    // ragged end (fewer samples than a group): one thread each
+    auto tail_index = [&]() { return ngroups * G + cta * kSmallThreads + threadIdx.x; };
+    auto load_tail = [&](uint32_t tail) -> float2 {
+        if constexpr (COHERENT) {
+            if constexpr (IN == I16)
+                return ingest_i16(__ldcv(reinterpret_cast<const uint32_t*>(a.in) + tail));
+            else
+                return __ldcv(reinterpret_cast<const float2*>(a.in) + tail);
+        } else {
+            return load_sample<IN>(a.in, tail);
+        }
+    };
+    auto tail_phasor = [&](uint32_t tail) -> float2 {
+        const DevPiece q = get_piece(a, find_piece(a, 0, tail));
+        return phasor(q.r, piece_samplenum(q, tail - q.k_begin));
+    };
+    float2 tail_smp = make_float2(0.f, 0.f), tail_ph = make_float2(0.f, 0.f);
+    bool tail_ready = false;
     for (uint32_t base = g_begin; base < g_end; base += kStep) {
         uint32_t w[V][4];
 #pragma unroll
@@ -1488,19 +1506,9 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
                 }
             }
         }
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-            const uint32_t g = base + v * kSmallThreads + threadIdx.x;
-            if (g >= g_end) break;
+        // the G phasors of group g: table entries, or direct evaluation where there is no table / a piece ends inside the group
+        auto phasors = [&](uint32_t g, float2 (&out)[G]) {
             const uint32_t k0 = g * G;
-            float2 smp[G], res[G];
-            if constexpr (IN == I16) {
-#pragma unroll
-                for (int i = 0; i < G; i++) smp[i] = ingest_i16(w[v][i]);
-            } else {
-                smp[0] = make_float2(__uint_as_float(w[v][0]), __uint_as_float(w[v][1]));
-                smp[1] = make_float2(__uint_as_float(w[v][2]), __uint_as_float(w[v][3]));
-            }
             if (k0 >= p.k_end) {
                 pi = find_piece(a, pi, k0);
                 p = get_piece(a, pi);
@@ -1509,7 +1517,7 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
                 // inside one tabled piece: entries j .. j+G-1 of its table (replicated kTabPad >= G-1 entries past the period)
                 const float2* tab = a.tables + p.tab + (piece_samplenum(p, k0 - p.k_begin) - 1u);
 #pragma unroll
-                for (int i = 0; i < G; i++) res[i] = cmul_unfused(smp[i], COHERENT ? __ldcg(tab + i) : __ldg(tab + i));
+                for (int i = 0; i < G; i++) out[i] = COHERENT ? __ldcg(tab + i) : __ldg(tab + i);
             } else {
                 uint32_t qi = pi;
                 DevPiece q = p;
@@ -1520,9 +1528,57 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
                         qi = find_piece(a, qi, k);
                         q = get_piece(a, qi);
                     }
-                    res[i] = cmul_unfused(smp[i], phasor(q.r, piece_samplenum(q, k - q.k_begin)));
+                    out[i] = phasor(q.r, piece_samplenum(q, k - q.k_begin));
                 }
             }
+        };
+        // The phasors do not depend on the input.  The resident kernel (one CTA, latency is all that counts) fetches them
+        // while the input is still on its way from host memory, instead of after it -- left to the compiler's scheduling the
+        // same source read 5.9 or 6.6 us per block from one build to the next.  The empty asm ties the input's first use to
+        // the phasors: everything above it is issued before anything waits for the input.  (The launched kernels keep the
+        // fused form: the extra live registers would cost them a resident CTA per SM.)
+        float2 ph[COHERENT ? V : 1][G];
+        if constexpr (COHERENT) {
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                const uint32_t g = base + v * kSmallThreads + threadIdx.x;
+#pragma unroll
+                for (int i = 0; i < G; i++) ph[v][i] = make_float2(0.f, 0.f);
+                if (g < g_end) phasors(g, ph[v]);
+            }
+            // (the ragged end's load and its generic evaluation too, so that nothing of a block is issued after the input has
+            //  arrived.  Blocks with a ragged end still cost ~2.4 us more than whole-group ones -- 2047 samples against 2048,
+            //  on every path, before and after this -- for a reason not found: profiles/r02_percall_mailbox_ab.txt)
+            if (!tail_ready && tail_index() < a.nsamples) {
+                tail_smp = load_tail(tail_index());
+                tail_ph = tail_phasor(tail_index());
+                tail_ready = true;
+            }
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                if constexpr (G == 4)
+                    asm volatile("" : "+r"(w[v][0]), "+r"(w[v][1]), "+r"(w[v][2]), "+r"(w[v][3])
+                                 : "f"(ph[v][0].x), "f"(ph[v][0].y), "f"(ph[v][1].x), "f"(ph[v][1].y), "f"(ph[v][2].x), "f"(ph[v][2].y), "f"(ph[v][3].x),
+                                   "f"(ph[v][3].y));
+                else
+                    asm volatile("" : "+r"(w[v][0]), "+r"(w[v][1]), "+r"(w[v][2]), "+r"(w[v][3]) : "f"(ph[v][0].x), "f"(ph[v][0].y), "f"(ph[v][1].x), "f"(ph[v][1].y));
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            const uint32_t g = base + v * kSmallThreads + threadIdx.x;
+            if (g >= g_end) break;
+            float2 smp[G], res[G];
+            if constexpr (IN == I16) {
+#pragma unroll
+                for (int i = 0; i < G; i++) smp[i] = ingest_i16(w[v][i]);
+            } else {
+                smp[0] = make_float2(__uint_as_float(w[v][0]), __uint_as_float(w[v][1]));
+                smp[1] = make_float2(__uint_as_float(w[v][2]), __uint_as_float(w[v][3]));
+            }
+            if constexpr (!COHERENT) phasors(g, ph[0]);
+#pragma unroll
+            for (int i = 0; i < G; i++) res[i] = cmul_unfused(smp[i], ph[COHERENT ? v : 0][i]);
             if constexpr (COHERENT) {
                 if constexpr (OUT == I16 && G == 4) {
                     store_units2(a.out, 4u * g, egress_i16(res[0]), egress_i16(res[1]), flag);
@@ -1542,21 +1598,13 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
             }
         }
     }
-    // ragged end (fewer samples than a group): one thread each
-    const uint32_t tail = ngroups * G + cta * kSmallThreads + threadIdx.x;
+    const uint32_t tail = tail_index();
     if (tail < a.nsamples) {
-        const uint32_t qi = find_piece(a, 0, tail);
-        const DevPiece q = get_piece(a, qi);
-        float2 smp;
-        if constexpr (COHERENT) {
-            if constexpr (IN == I16)
-                smp = ingest_i16(__ldcv(reinterpret_cast<const uint32_t*>(a.in) + tail));
-            else
-                smp = __ldcv(reinterpret_cast<const float2*>(a.in) + tail);
-        } else {
-            smp = load_sample<IN>(a.in, tail);
+        if (!tail_ready) {
+            tail_smp = load_tail(tail);
+            tail_ph = tail_phasor(tail);
         }
-        const float2 res = cmul_unfused(smp, phasor(q.r, piece_samplenum(q, tail - q.k_begin)));
+        const float2 res = cmul_unfused(tail_smp, tail_ph);
         if constexpr (!COHERENT)
             store_sample<OUT>(a.out, tail, res);
         else if constexpr (OUT == I16)
@@ -1597,11 +1645,14 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
 //             staging buffer and writes every 32-bit word of the result next to the request number
 //     host:   collects the result: a word is there when its neighbour shows n
 // What a block costs is PCIe round trips (~2 us each), so the protocol is built to need few of them:
-//   * A request is TWO 64-byte lines whose last word is the request number: head word (types, number of pieces), sample count,
-//     up to kRtPieces pieces of 8 words, the sum of those words.  The buffers' addresses travel with the launch, not with the
-//     request.  The host writes a line's payload before its tag (x86 stores are ordered), a read of a line returns a coherent
-//     snapshot, and the CTA takes the request when both tags show the same new number and the words add up -- the sum covers
-//     what nothing promises, that a line is fetched in one piece rather than as two 32-byte sectors at different times.
+//   * A request is 128 bytes: four 32-byte SECTORS of seven payload words and a tag, the request number -- head word (types,
+//     number of pieces), sample count, up to kRtPieces pieces of 8 words.  The buffers' addresses travel with the launch, not
+//     with the request.  A sector is the unit the memory system fetches, so a read of one is a coherent snapshot; the host
+//     writes a sector's payload before its tag (x86 stores are ordered), so a sector whose tag is n carries request n, and the
+//     CTA takes the request when all four tags show the same new number.  (An earlier version tagged 64-byte lines and added
+//     the sum of the words against a line being fetched as two sectors at different times; a sum does not tell a block of
+//     2048 samples at base 100 from one of 2047 at base 101.  Tags per sector need no such argument and cost nothing: the
+//     layouts interleaved on one box read 5.84-5.94 us per block either way, profiles/r02_percall_mailbox_ab.txt.)
 //   * One look at a time, by warp 0 alone while the other warps wait at a barrier.  (Keeping four looks in flight, issued a
 //     fraction of a microsecond apart so that a request need not wait for the previous look to return, was measured and LOST
 //     3.4 us per block: reads of host memory still in flight delay the block's own reads.  With blocks sent back to back the
@@ -1614,24 +1665,24 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
 // on a quit request; the host starts another when it finds alive == 0.  Only plans of up to kRtPieces pieces come here.
 constexpr int kRtPieces = 3;
 constexpr int kRtPieceWords = 8;                                     // DevPiece up to and including `shift` (small_body reads no more)
-constexpr int kRtPayloadWords = 2 + kRtPieces * kRtPieceWords + 1;   // head, nsamples, pieces, checksum (last)
-constexpr int kRtLines = 2;
+constexpr int kRtPayloadWords = 2 + kRtPieces * kRtPieceWords;       // head, nsamples, pieces
+constexpr int kRtSectors = 4;                                        // of 7 payload words + tag
 constexpr uint32_t kRtQuit = 0x80000000u;                            // head word: leave now
 constexpr uint32_t kRtLast = 0x40000000u;                            // (device only) this request came with the last look
-struct RtLine {
-    uint32_t w[15];
+struct RtSector {
+    uint32_t w[7];
     uint32_t tag;
 };
 struct RtMailbox {
-    RtLine req[kRtLines];       // host -> device
+    RtSector req[kRtSectors];   // host -> device
     volatile uint32_t alive;    // generation of the resident kernel (the host writes it before the launch); the kernel clears it when it leaves
     uint32_t pad0[15];
     volatile uint32_t served;   // device -> its successor: the latest request taken (a kernel that starts behind one that was still
                                 // leaving must not take that one's last request again); the host never reads it (its own line)
     uint32_t pad1[15];
 };
-static_assert(sizeof(RtLine) == 64 && kRtLines * 16 == 32, "the mailbox is one warp-wide read");
-static_assert(kRtPayloadWords <= kRtLines * 15, "the request fits its lines");
+static_assert(sizeof(RtSector) == 32 && kRtSectors * 8 == 32, "the mailbox is one warp-wide read");
+static_assert(kRtPayloadWords <= kRtSectors * 7, "the request fits its sectors");
 static_assert(kRtPieces <= kInlinePieces && kRtPieceWords * 4 <= (int)offsetof(DevPiece, step_u), "pieces travel up to `shift`");
 
 // head word of a request
@@ -1644,21 +1695,13 @@ __device__ __forceinline__ uint64_t global_timer_ns()
     return t;
 }
 
-// One look's verdict, computed by the whole warp from the word each lane read: the request number if the lines hold one whole
-// request other than `last`, else `last`.
-__device__ __forceinline__ uint32_t rt_verdict(uint32_t v, uint32_t lane, uint32_t last)
+// One look's verdict, computed by the whole warp from the word each lane read: the request number if the four sectors hold one
+// whole request other than `last`, else `last`.
+__device__ __forceinline__ uint32_t rt_verdict(uint32_t v, uint32_t last)
 {
-    const uint32_t tag0 = __shfl_sync(0xffffffffu, v, 15), tag1 = __shfl_sync(0xffffffffu, v, 31);
-    const uint32_t w = (lane >> 4) * 15u + (lane & 15u);   // payload index of this lane's word (tags aside)
-    int contrib = 0;
-    if ((lane & 15u) != 15u) {
-        if (w < (uint32_t)kRtPayloadWords - 1u)
-            contrib = (int)v;
-        else if (w == (uint32_t)kRtPayloadWords - 1u)
-            contrib = -(int)v;
-    }
-    const int total = __reduce_add_sync(0xffffffffu, contrib);
-    return (tag0 == tag1 && total == 0) ? tag0 : last;
+    const uint32_t t0 = __shfl_sync(0xffffffffu, v, 7), t1 = __shfl_sync(0xffffffffu, v, 15);
+    const uint32_t t2 = __shfl_sync(0xffffffffu, v, 23), t3 = __shfl_sync(0xffffffffu, v, 31);
+    return (t0 == t1 && t0 == t2 && t0 == t3) ? t0 : last;
 }
 
 static __global__ void __launch_bounds__(kSmallThreads, 1)
@@ -1689,7 +1732,7 @@ mix_resident_kernel(RtMailbox* mb, const void* in, void* out_units, const float2
             const uint64_t t0 = global_timer_ns();
             for (;;) {   // one look at a time (see above)
                 v = words[tid];
-                seq = rt_verdict(v, tid, last);
+                seq = rt_verdict(v, last);
                 if (seq != last) break;
                 if (__shfl_sync(0xffffffffu, global_timer_ns() - t0 > idle_ns ? 1 : 0, 0)) {   // (lane 0's clock: one verdict for the warp)
                     leave = true;
@@ -1704,18 +1747,18 @@ mix_resident_kernel(RtMailbox* mb, const void* in, void* out_units, const float2
                 }
                 __syncwarp();
                 v = words[tid];
-                seq = rt_verdict(v, tid, last);
+                seq = rt_verdict(v, last);
             }
             if (seq != last) {
-                const uint32_t w = (tid >> 4) * 15u + (tid & 15u);
-                if ((tid & 15u) != 15u) {
+                const uint32_t w = (tid >> 3) * 7u + (tid & 7u);   // payload index of this lane's word (tags aside)
+                if ((tid & 7u) != 7u) {
                     if (w == 0) {
                         s_head = leave ? (v | kRtLast) : v;
                         s_seq = seq;
                         s_args.npieces = (v >> 2) & 7u;
                     } else if (w == 1) {
                         s_args.nsamples = v;
-                    } else if (w < (uint32_t)kRtPayloadWords - 1u) {
+                    } else if (w < (uint32_t)kRtPayloadWords) {
                         const uint32_t pw = w - 2u;
                         reinterpret_cast<uint32_t*>(&s_args.inl[pw / kRtPieceWords])[pw % kRtPieceWords] = v;
                     }

@@ -81,3 +81,14 @@ def test_units_arriving_in_any_order(lib):
             assert np.array_equal(out[:now], new[:now])
             got = now
     assert got == n
+
+
+@pytest.mark.parametrize("first_seq", [1, 0xFFFFFF00])
+def test_hand_over_against_a_software_device(lib, first_seq):
+    """The product's host code (post + collect) against a thread that plays the resident kernel's side of the protocol and is
+    harsher than the device: it reads the request lines word by word in a random order and writes the result units in a random
+    order.  Every request is taken whole, exactly once and in order, and no stale word is ever handed out -- also across the
+    wrap of the 32-bit request number."""
+    lib.hostcheck_handover.restype = ctypes.c_int
+    lib.hostcheck_handover.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32]
+    assert lib.hostcheck_handover(3000, 2048, 12345 + first_seq % 7, first_seq) == 0

@@ -20,7 +20,8 @@ int main()
     }
     auto now = [] { return std::chrono::steady_clock::now(); };
     const bool quick = getenv("PERCALL_QUICK") != nullptr;   // bench.py: the 8192-byte block only, resident kernel vs launch per block
-    const std::vector<size_t> sizes = quick ? std::vector<size_t>{2048} : std::vector<size_t>{1024, 2048, 16384, 262144, 4194304, 33554432};   // complex samples per call
+    const size_t quick_n = getenv("PERCALL_N") ? (size_t)atol(getenv("PERCALL_N")) : 2048;   // (2047: the plan differs from block to block)
+    const std::vector<size_t> sizes = quick ? std::vector<size_t>{quick_n} : std::vector<size_t>{1024, 2048, 16384, 262144, 4194304, 33554432};   // complex samples per call
     for (int mode = 2; mode >= (quick ? 1 : 0); mode--) {   // 2: resident kernel (blocks up to 32 KiB), 1: one zero-copy launch per block, 0: staged pipeline
         const int tiny = mode >= 1;
         doppler_b200_tune(ctx, DOPPLER_B200_TUNE_TINY_HOST_BYTES, tiny ? (128u << 10) : 0);
@@ -65,7 +66,7 @@ int main()
     for (int mode = 2; mode >= 1; mode--) {
         doppler_b200_tune(ctx, DOPPLER_B200_TUNE_TINY_HOST_BYTES, 128u << 10);
         doppler_b200_tune(ctx, DOPPLER_B200_TUNE_RESIDENT_IDLE_US, mode == 2 ? 20000 : 0);
-        const size_t n = 2048, bytes = n * 4;
+        const size_t n = quick ? quick_n : 2048, bytes = n * 4;
         void *in = malloc(bytes), *out = malloc(bytes);
         memset(in, 1, bytes);
         uint32_t sn = 0, lcg = 12345;
