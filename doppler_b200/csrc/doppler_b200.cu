@@ -165,6 +165,10 @@ struct doppler_b200_ctx {
         uint32_t r_bits = 0;
         DevPiece piece;   // period, r, tab, magic, shift of that plan (k_begin .. base are per block)
     } rt_steady;
+    // The ratio of the previous per-block host call (one shift): a block stream that keeps its ratio gets a phasor table even
+    // when ONE block is shorter than two periods -- the table pays across the calls (launch_mix, tiny_host_call).
+    bool tiny_last_r_valid = false;
+    uint32_t tiny_last_r_bits = 0;
     uint64_t rt_traced = 0, rt_steady_traced = 0;
     uint64_t rt_steady_ns[3] = {0, 0, 0};   // the same for calls planned by the steady-state rule (tiny_host_call)
     uint64_t rt_ns[3] = {0, 0, 0};          // DOPPLER_B200_TRACE=1: stage in, plan, request -> result collected in the caller's buffer (resident-kernel calls only)
@@ -577,7 +581,11 @@ int launch_mix(doppler_b200_ctx* ctx, const void* d_in, void* d_out, uint64_t ns
         for (size_t i = 0; i < dev.size(); i++) {
             dev_len.push_back(dev[i].k_end - dev[i].k_begin);
             if (dev[i].period) {
-                int rc = get_table(ctx, dev[i].r, dev[i].period, src[i]->k_end - src[i]->k_begin, s, &dev[i].tab);
+                uint64_t reuse = src[i]->k_end - src[i]->k_begin;   // samples that will read the table
+                uint32_t r_bits;
+                memcpy(&r_bits, &dev[i].r, 4);
+                if (done && ctx->tiny_last_r_valid && r_bits == ctx->tiny_last_r_bits) reuse = std::max<uint64_t>(reuse, 2ull * dev[i].period);
+                int rc = get_table(ctx, dev[i].r, dev[i].period, reuse, s, &dev[i].tab);
                 if (rc) return rc;
             }
         }
@@ -1061,6 +1069,15 @@ int tiny_host_call(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int
         runs.push_back(dplan::Run{nsamples, dplan::ratio(shifts[0], samplerate)});
     else
         runs = dplan::runs_from_blocks(shifts, nblocks, block_samples, samplerate, nsamples);
+    struct NoteRatio {   // on every way out: what ratio this call had (one shift), for the next call's table decision
+        doppler_b200_ctx* ctx;
+        const std::vector<dplan::Run>& runs;
+        ~NoteRatio()
+        {
+            ctx->tiny_last_r_valid = runs.size() == 1;
+            if (ctx->tiny_last_r_valid) memcpy(&ctx->tiny_last_r_bits, &runs[0].r, 4);
+        }
+    } note_ratio{ctx, runs};
     const uint32_t token = ++ctx->done_token ? ctx->done_token : ++ctx->done_token;   // never 0
     const dmix::SmallDone done{ctx->done_counter, ctx->done_flag_dev, token};
     // staged blocks (the reference's 8192-byte pump block) go to the resident kernel when their plan fits its mailbox
@@ -1079,7 +1096,10 @@ int tiny_host_call(doppler_b200_ctx* ctx, const void* in, uint64_t nsamples, int
         const auto t_2r = std::chrono::steady_clock::now();
         rc = rt_request(ctx, rt_args, intype, outtype, out, nsamples * obps / 4);   // (collects the result straight into `out`)
         if (rc) return rc;
-        ctx->rt_steady.valid = !ctx->rt_steady.off && runs.size() == 1 && rt_args.npieces == 1 && rt_args.inl[0].period != 0;
+        // (a piece that could have a table but has none yet -- the first block of a ratio -- goes through launch_mix once more,
+        //  which builds the table on second sight)
+        ctx->rt_steady.valid = !ctx->rt_steady.off && runs.size() == 1 && rt_args.npieces == 1 && rt_args.inl[0].period != 0 &&
+                               (rt_args.inl[0].tab != dmix::kNoTab || rt_args.inl[0].period > kSmemTabMaxEntries);
         if (ctx->rt_steady.valid) {
             ctx->rt_steady.piece = rt_args.inl[0];
             memcpy(&ctx->rt_steady.r_bits, &rt_args.inl[0].r, 4);

@@ -1547,8 +1547,8 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
                 if (g < g_end) phasors(g, ph[v]);
             }
             // (the ragged end's load and its generic evaluation too, so that nothing of a block is issued after the input has
-            //  arrived.  Blocks with a ragged end still cost ~2.4 us more than whole-group ones -- 2047 samples against 2048,
-            //  on every path, before and after this -- for a reason not found: profiles/r02_percall_mailbox_ab.txt)
+            //  arrived.  Blocks with a ragged end still cost ~1.6 us more than whole-group ones -- 2047 samples against 2048 --
+            //  for a reason not found: profiles/r02_percall_mailbox_ab.txt)
             if (!tail_ready && tail_index() < a.nsamples) {
                 tail_smp = load_tail(tail_index());
                 tail_ph = tail_phasor(tail_index());

@@ -207,3 +207,27 @@ def test_kernel_leaves_before_a_persistent_launch(oracle, fresh):
     mid = fresh.launch_count
     got, _ = fresh.mix(blk, I16, I16, 5000.0, 1_024_000, samplenum=7)
     assert np.array_equal(got, want_blk) and fresh.launch_count == mid + 1         # a new resident kernel
+
+
+def test_block_stream_shorter_than_two_periods_gets_its_table(oracle, fresh):
+    """P = 1024 and blocks of 2047 / 1500 / 2048 samples: one block alone would not pay for a phasor table (fewer than two
+    periods), the stream does -- built on the second block of the ratio, read by every block after it.  Bytes as the oracle's
+    either way; the table shows as exactly one more launch."""
+    rng = np.random.default_rng(71)
+    fs = 1_024_000
+    for n in (2047, 1500, 2048):
+        m = doppler_b200.Mixer(0)
+        try:
+            sn_g = sn_o = 0
+            counts = []
+            for b in range(12):
+                buf = make_input(rng, n, I16)
+                before = m.launch_count
+                got, sn_g = m.mix(buf, I16, I16, 5000.0, fs, samplenum=sn_g)
+                want, sn_o = oracle.mix(buf, I16, I16, 5000.0, fs, samplenum=sn_o)
+                assert sn_g == sn_o and np.array_equal(got, want), (n, b)
+                counts.append(m.launch_count - before)
+            assert sum(counts[3:]) == 0, counts          # steady: no launches at all
+            assert 2 <= sum(counts[:3]) <= 4, counts     # the resident kernel, the table (and a restart once the arena exists)
+        finally:
+            m.close()
