@@ -1484,7 +1484,12 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
     };
     auto tail_phasor = [&](uint32_t tail) -> float2 {
         const DevPiece q = get_piece(a, find_piece(a, 0, tail));
-        return phasor(q.r, piece_samplenum(q, tail - q.k_begin));
+        const uint32_t n = piece_samplenum(q, tail - q.k_begin);
+        if (q.tab != kNoTab) {   // the piece's table holds the same bits, and reading it is no call with the groups' loads in flight
+            const float2* e = a.tables + q.tab + (n - 1u);
+            return COHERENT ? __ldcg(e) : __ldg(e);
+        }
+        return phasor(q.r, n);
     };
     float2 tail_smp = make_float2(0.f, 0.f), tail_ph = make_float2(0.f, 0.f);
     bool tail_ready = false;
@@ -1546,9 +1551,7 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
                 for (int i = 0; i < G; i++) ph[v][i] = make_float2(0.f, 0.f);
                 if (g < g_end) phasors(g, ph[v]);
             }
-            // (the ragged end's load and its generic evaluation too, so that nothing of a block is issued after the input has
-            //  arrived.  Blocks with a ragged end still cost ~1.6 us more than whole-group ones -- 2047 samples against 2048 --
-            //  for a reason not found: profiles/r02_percall_mailbox_ab.txt)
+            // (the ragged end's load and phasor too, so that nothing of a block is issued after the input has arrived)
             if (!tail_ready && tail_index() < a.nsamples) {
                 tail_smp = load_tail(tail_index());
                 tail_ph = tail_phasor(tail_index());
