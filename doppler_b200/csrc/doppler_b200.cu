@@ -889,6 +889,7 @@ int device_alias(doppler_b200_ctx* ctx, const void* host, void** dev)
 }
 
 // ---- resident kernel (mixer_kernels.cuh: mix_resident_kernel) --------------------------------------------------------------
+static_assert(kTinyStageBytes == (size_t)dmix::kRtStageBytes, "the resident kernel stages a whole block in shared memory");
 constexpr size_t kRtOutUnits = 2 * kTinyStageBytes / 4;   // result words of the largest block served (i16 -> f32 doubles the bytes)
 
 // A kernel that reads blocks at `in_dev` and tables at `tables_dev`, and has served every request up to ctx->rt_seq (`pending`:

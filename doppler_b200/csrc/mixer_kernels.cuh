@@ -1458,10 +1458,19 @@ __device__ __forceinline__ void store_unit(void* units, uint32_t unit, uint32_t 
 
 // COHERENT also changes where the result goes: a.out is an array of 8-byte UNITS, unit u = {word u of the result, `flag`}
 // (the resident kernel's fence-free hand-over: the host takes a word when its flag shows the request number).
+// STAGE (resident kernel, 16-byte groups): the input does not travel into registers but, by cp.async, into `stage` (shared memory,
+// 16 bytes per group of the block).  A block without a table evaluates its phasors with the generic routine -- calls -- and
+// around a call the compiler parks the registers that loads are in flight to, which waits for the loads: the ~2.4 us of
+// evaluation ran after the round trip to host memory instead of under it.  With the input on its way to shared memory no
+// register is pending: 9.6 -> 8.7 us per table-less block (10.2 -> 9.0 paced) -- the case of realtime track mode, a new ratio
+// for every block, and of any shift whose period is beyond a table.  Blocks whose pieces all have tables pay 0.3 us for the
+// detour (7.17 -> 7.44 on the same box); choosing per block at run time was measured and is worse for both (7.77 / 9.54: both
+// forms in one body cost registers and scheduling).  profiles/r02_percall_mailbox_ab.txt
 template <int IN, int OUT, int V, bool COHERENT>
-__device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint32_t nctas, uint32_t flag = 0)
+__device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint32_t nctas, uint32_t flag = 0, unsigned char* stage = nullptr)
 {
     constexpr int G = group_samples(IN, OUT);
+    constexpr bool kStaged = COHERENT && !(IN == I16 && G == 2);   // (cp.async past L1 moves 16 bytes; the 8-byte groups stay in registers)
     constexpr uint32_t kStep = kSmallThreads * V;
     const uint32_t ngroups = a.nsamples / G;
     uint32_t pi = 0;
@@ -1499,7 +1508,12 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
         for (int v = 0; v < V; v++) {
             const uint32_t g = base + v * kSmallThreads + threadIdx.x;
             w[v][0] = w[v][1] = w[v][2] = w[v][3] = 0;
-            if (g < g_end) {
+            if constexpr (kStaged) {
+                if (g < g_end)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stage + 16u * (g - g_begin))),
+                                 "l"(reinterpret_cast<const uint4*>(a.in) + g)
+                                 : "memory");
+            } else if (g < g_end) {
                 if constexpr (IN == I16 && G == 2) {
                     const uint2* src = reinterpret_cast<const uint2*>(a.in) + g;
                     const uint2 x = COHERENT ? __ldcv(src) : __ldcs(src);
@@ -1511,6 +1525,7 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
                 }
             }
         }
+        if constexpr (kStaged) asm volatile("cp.async.commit_group;" ::: "memory");
         // the G phasors of group g: table entries, or direct evaluation where there is no table / a piece ends inside the group
         auto phasors = [&](uint32_t g, float2 (&out)[G]) {
             const uint32_t k0 = g * G;
@@ -1557,8 +1572,19 @@ __device__ __forceinline__ void small_body(const MixArgs& a, uint32_t cta, uint3
                 tail_ph = tail_phasor(tail_index());
                 tail_ready = true;
             }
+            if constexpr (kStaged) {
+                asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's copies have landed: it reads back only what it copied
 #pragma unroll
-            for (int v = 0; v < V; v++) {
+                for (int v = 0; v < V; v++) {
+                    const uint32_t g = base + v * kSmallThreads + threadIdx.x;
+                    if (g < g_end) {
+                        const uint4 x = *reinterpret_cast<const uint4*>(stage + 16u * (g - g_begin));
+                        w[v][0] = x.x, w[v][1] = x.y, w[v][2] = x.z, w[v][3] = x.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int v = 0; !kStaged && v < V; v++) {
                 if constexpr (G == 4)
                     asm volatile("" : "+r"(w[v][0]), "+r"(w[v][1]), "+r"(w[v][2]), "+r"(w[v][3])
                                  : "f"(ph[v][0].x), "f"(ph[v][0].y), "f"(ph[v][1].x), "f"(ph[v][1].y), "f"(ph[v][2].x), "f"(ph[v][2].y), "f"(ph[v][3].x),
@@ -1666,6 +1692,7 @@ __global__ void __launch_bounds__(kSmallThreads) mix_small_kernel(const __grid_c
 //     a flag costs a round trip of ~3 us on top of the 16 KB this writes instead of 8.
 // The kernel leaves by itself after `idle_ns` without a request (alive = 0, then one last look issued after that), and at once
 // on a quit request; the host starts another when it finds alive == 0.  Only plans of up to kRtPieces pieces come here.
+constexpr int kRtStageBytes = 32 << 10;                              // the largest block the resident kernel serves (doppler_b200.cu: kTinyStageBytes)
 constexpr int kRtPieces = 3;
 constexpr int kRtPieceWords = 8;                                     // DevPiece up to and including `shift` (small_body reads no more)
 constexpr int kRtPayloadWords = 2 + kRtPieces * kRtPieceWords;       // head, nsamples, pieces
@@ -1712,6 +1739,7 @@ mix_resident_kernel(RtMailbox* mb, const void* in, void* out_units, const float2
 {
     __shared__ MixArgs s_args;
     __shared__ uint32_t s_head, s_seq;
+    __shared__ __align__(16) unsigned char s_stage[kRtStageBytes];   // the block's input on its way in (small_body: STAGE)
     const uint32_t tid = threadIdx.x;
     const volatile uint32_t* words = reinterpret_cast<const volatile uint32_t*>(mb);
     {
@@ -1777,10 +1805,10 @@ mix_resident_kernel(RtMailbox* mb, const void* in, void* out_units, const float2
         last = s_seq;
         if (tid == 0) mb->served = last;
         switch (head & 3u) {
-        case 0: small_body<I16, I16, 4, true>(s_args, 0, 1, last); break;
-        case 1: small_body<I16, F32, 4, true>(s_args, 0, 1, last); break;
-        case 2: small_body<F32, I16, 4, true>(s_args, 0, 1, last); break;
-        default: small_body<F32, F32, 4, true>(s_args, 0, 1, last); break;
+        case 0: small_body<I16, I16, 4, true>(s_args, 0, 1, last, s_stage); break;
+        case 1: small_body<I16, F32, 4, true>(s_args, 0, 1, last, s_stage); break;
+        case 2: small_body<F32, I16, 4, true>(s_args, 0, 1, last, s_stage); break;
+        default: small_body<F32, F32, 4, true>(s_args, 0, 1, last, s_stage); break;
         }
         if (head & kRtLast) break;   // (served after the departure was announced: the host will start a successor)
         __syncthreads();             // s_args / s_head are rewritten by the next request
