@@ -926,7 +926,7 @@ int rt_start(doppler_b200_ctx* ctx, const void* in_dev, const void* tables_dev, 
     return DOPPLER_B200_OK;
 }
 
-// A request in the mailbox's tagged lines: payload first, then the line's tag (mixer_kernels.cuh: RtMailbox).
+// A request in the mailbox's tagged sectors: payload first, then the sector's tag (mixer_kernels.cuh: RtMailbox; collect.cpp: post).
 static uint32_t rt_post(doppler_b200_ctx* ctx, uint32_t head, const MixArgs* a)
 {
     uint32_t payload[dmix::kRtPayloadWords] = {0};
