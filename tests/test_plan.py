@@ -247,3 +247,29 @@ def test_libm_guard(oracle):
 
     cb = CB(other)
     assert lib.doppler_b200_libm_mismatches(ctypes.cast(cb, ctypes.c_void_p)) > 0
+
+
+def test_steady_state_rule_of_the_per_block_path(oracle):
+    """tiny_host_call (doppler_b200.cu) plans a block of an unchanged ratio without the planner when samplenum is inside the
+    ratio's period P: ONE periodic piece with base = samplenum - 1, i.e. sample k uses ((samplenum - 1 + k) mod P) + 1, and
+    the state afterwards is ((samplenum - 1 + n) mod P) + 1.  Pinned here against the oracle's sequential recurrence and the
+    planner, for regular and irregular ratios, every kind of start inside the period and ragged block lengths."""
+    rng = np.random.default_rng(2026)
+    for shift, fs in [(5000.0, 1_024_000), (-15000.0, 256000), (100000.0, 10_000_000), (7321.7, 1_024_000), (-9876.54, 1_024_000)]:
+        # the period: the state right after the first reset counts 1 .. P
+        first, _ = oracle.samplenum_trace(1, shift, fs, 400_000)
+        resets = np.flatnonzero(first[1:] == 1)
+        assert resets.size, (shift, fs)
+        P = int(first[resets[0]])                        # the value that hit
+        starts = [1, 2, P - 1, P] + [int(x) for x in rng.integers(1, P + 1, 6)]
+        for sn in starts:
+            for n in (1, 3, 2047, 2048, 8192, int(rng.integers(1, 3 * P + 10))):
+                want, sn_want = oracle.samplenum_trace(sn, shift, fs, n)
+                k = np.arange(n, dtype=np.uint64)
+                rule = ((np.uint64(sn - 1) + k) % np.uint64(P) + 1).astype(np.uint32)
+                assert np.array_equal(rule, want), (shift, fs, sn, n)
+                assert ((sn - 1 + n) % P) + 1 == sn_want
+                got, sn_got, npieces = dsp.plan_trace(sn, [shift], n, fs, n)
+                assert np.array_equal(got, want) and sn_got == sn_want
+                # (the planner has to learn the period first: it may need a piece per period until a stream that started
+                #  at a reset has shown it -- the per-block path takes its shortcut only from a plan that was one periodic piece)
