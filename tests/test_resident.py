@@ -217,6 +217,7 @@ def test_block_stream_shorter_than_two_periods_gets_its_table(oracle, fresh):
     fs = 1_024_000
     for n in (2047, 1500, 2048):
         m = doppler_b200.Mixer(0)
+        m.tune(resident_idle_us=5_000_000)               # (a pause on a busy box must not show up as a kernel start below)
         try:
             sn_g = sn_o = 0
             counts = []
