@@ -122,3 +122,9 @@ extern "C" int hostcheck_handover(int requests, int max_words, uint32_t seed, ui
     if (rc == 0 && served_count.load() != (uint32_t)requests) rc = -3;
     return rc;
 }
+
+// the request layout as posted (dcollect::post): 32 words for four sectors
+extern "C" void hostcheck_post(uint32_t* mailbox, int sectors, uint32_t seq, const uint32_t* payload, int payload_words)
+{
+    dcollect::post(mailbox, sectors, seq, payload, payload_words);
+}

@@ -92,3 +92,21 @@ def test_hand_over_against_a_software_device(lib, first_seq):
     lib.hostcheck_handover.restype = ctypes.c_int
     lib.hostcheck_handover.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32]
     assert lib.hostcheck_handover(3000, 2048, 12345 + first_seq % 7, first_seq) == 0
+
+
+def test_request_layout(lib):
+    """dcollect::post against the layout the kernel reads (mixer_kernels.cuh: RtMailbox, rt_verdict): four 32-byte sectors, seven
+    payload words each in order, the request number as every sector's eighth word, zeros behind the payload."""
+    lib.hostcheck_post.restype = None
+    lib.hostcheck_post.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int]
+    payload = np.arange(1000, 1026, dtype=np.uint32)            # head, nsamples, three pieces of eight words
+    box = np.full(32, 0xDEADBEEF, np.uint32)
+    lib.hostcheck_post(box.ctypes.data, 4, 77, payload.ctypes.data, payload.size)
+    assert list(box[7::8]) == [77, 77, 77, 77]
+    body = np.concatenate([box[8 * t:8 * t + 7] for t in range(4)])
+    assert np.array_equal(body[:26], payload) and not body[26:].any()
+    # lane -> payload index as the kernel computes it: (lane >> 3) * 7 + (lane & 7) for the lanes that are not tags
+    for lane in range(32):
+        if lane & 7 != 7:
+            w = (lane >> 3) * 7 + (lane & 7)
+            assert box[lane] == (payload[w] if w < 26 else 0)
